@@ -1,0 +1,189 @@
+// BLS12-381 group arithmetic on the device: Fq2 and short-Weierstrass points (a = 0) in
+// affine and extended-Jacobian "XYZZ" coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2).
+//
+// Replaces ark-ec 0.3 `short_weierstrass_jacobian` (un-vendored upstream).  ark
+// accumulates MSM buckets with the Jacobian mixed add (7M + 4S); XYZZ needs 8M + 2S and no
+// per-step doubling of temporaries, and any coordinate system yields the same affine point, which is
+// all that is observable in the proof bytes.
+//
+// Generic over the coordinate field F (Fq for G1, Fq2 for G2).
+#pragma once
+#include "fp.cuh"
+
+namespace mp {
+
+// ---- Fq2 = Fq[u]/(u^2 + 1) -------------------------------------------------------------------------
+struct Fq2 {
+    Fq c0, c1;
+    static constexpr int WORDS = 24;
+
+    MP_DEV static Fq2 zero() { return {Fq::zero(), Fq::zero()}; }
+    MP_DEV static Fq2 one() { return {Fq::one(), Fq::zero()}; }
+    MP_DEV static Fq2 load(const void* p) {
+        return {Fq::load(p), Fq::load(reinterpret_cast<const uint32_t*>(p) + 12)};
+    }
+    MP_DEV static Fq2 load_ro(const void* p) {
+        return {Fq::load_ro(p), Fq::load_ro(reinterpret_cast<const uint32_t*>(p) + 12)};
+    }
+    MP_DEV void store(void* p) const {
+        c0.store(p);
+        c1.store(reinterpret_cast<uint32_t*>(p) + 12);
+    }
+    MP_DEV bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    MP_DEV bool operator==(const Fq2& o) const { return c0 == o.c0 && c1 == o.c1; }
+    MP_DEV bool operator!=(const Fq2& o) const { return !(*this == o); }
+    MP_DEV Fq2 operator+(const Fq2& o) const { return {c0 + o.c0, c1 + o.c1}; }
+    MP_DEV Fq2 operator-(const Fq2& o) const { return {c0 - o.c0, c1 - o.c1}; }
+    MP_DEV Fq2 neg() const { return {c0.neg(), c1.neg()}; }
+    MP_DEV Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
+    MP_DEV Fq2 operator*(const Fq2& o) const {  // Karatsuba: 3 Fq products
+        Fq t0 = c0 * o.c0;
+        Fq t1 = c1 * o.c1;
+        Fq t2 = (c0 + c1) * (o.c0 + o.c1);
+        return {t0 - t1, t2 - t0 - t1};
+    }
+    MP_DEV Fq2 sqr() const {  // (c0 + c1)(c0 - c1), 2 c0 c1
+        Fq t = c0 * c1;
+        return {(c0 + c1) * (c0 - c1), t.dbl()};
+    }
+    MP_COLD Fq2 inv() const {
+        Fq n = (c0.sqr() + c1.sqr()).inv();
+        return {c0 * n, (c1 * n).neg()};
+    }
+    MP_DEV static Fq2 select(bool c, const Fq2& a, const Fq2& b) {
+        return {Fq::select(c, a.c0, b.c0), Fq::select(c, a.c1, b.c1)};
+    }
+    MP_DEV Fq2 from_mont() const { return {c0.from_mont(), c1.from_mont()}; }
+    MP_DEV Fq2 to_mont() const { return {c0.to_mont(), c1.to_mont()}; }
+};
+
+template <class F> struct FieldWords;
+template <> struct FieldWords<Fq> { static constexpr int W = 12; };
+template <> struct FieldWords<Fq2> { static constexpr int W = 24; };
+
+// ---- points ------------------------------------------------------------------------------------------
+// Affine point; (0, 0) encodes the point at infinity (never on y^2 = x^3 + b, b != 0).
+template <class F>
+struct Affine {
+    F x, y;
+    static constexpr int WORDS = 2 * FieldWords<F>::W;
+    MP_DEV static Affine load(const void* p) {
+        return {F::load(p), F::load(reinterpret_cast<const uint32_t*>(p) + FieldWords<F>::W)};
+    }
+    MP_DEV static Affine load_ro(const void* p) {
+        return {F::load_ro(p), F::load_ro(reinterpret_cast<const uint32_t*>(p) + FieldWords<F>::W)};
+    }
+    MP_DEV void store(void* p) const {
+        x.store(p);
+        y.store(reinterpret_cast<uint32_t*>(p) + FieldWords<F>::W);
+    }
+    MP_DEV bool is_inf() const { return x.is_zero() && y.is_zero(); }
+    MP_DEV static Affine inf() { return {F::zero(), F::zero()}; }
+    MP_DEV Affine neg() const { return {x, y.neg()}; }
+};
+
+// Extended Jacobian; ZZ == 0 encodes infinity.
+template <class F>
+struct XYZZ {
+    F X, Y, ZZ, ZZZ;
+    static constexpr int WORDS = 4 * FieldWords<F>::W;
+
+    MP_DEV static XYZZ inf() { return {F::zero(), F::zero(), F::zero(), F::zero()}; }
+    MP_DEV bool is_inf() const { return ZZ.is_zero(); }
+    MP_DEV static XYZZ from_affine(const Affine<F>& p) {
+        if (p.is_inf()) return inf();
+        return {p.x, p.y, F::one(), F::one()};
+    }
+    MP_DEV static XYZZ load(const void* p) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+        constexpr int W = FieldWords<F>::W;
+        return {F::load(q), F::load(q + W), F::load(q + 2 * W), F::load(q + 3 * W)};
+    }
+    MP_DEV void store(void* p) const {
+        uint32_t* q = reinterpret_cast<uint32_t*>(p);
+        constexpr int W = FieldWords<F>::W;
+        X.store(q); Y.store(q + W); ZZ.store(q + 2 * W); ZZZ.store(q + 3 * W);
+    }
+    MP_DEV XYZZ neg() const { return {X, Y.neg(), ZZ, ZZZ}; }
+
+    // dbl-2008-s-1 (a = 0): 6M + 4S... counted as 2M + 5S + small ops below
+    MP_COLD XYZZ dbl() const {
+        if (is_inf()) return *this;
+        F U = Y.dbl();
+        F V = U.sqr();
+        F W = U * V;
+        F S = X * V;
+        F M = X.sqr();
+        M = M.dbl() + M;
+        F X3 = M.sqr() - S.dbl();
+        F Y3 = M * (S - X3) - W * Y;
+        return {X3, Y3, V * ZZ, W * ZZZ};
+    }
+    // doubling of an affine point (mdbl-2008-s-1)
+    MP_COLD static XYZZ dbl_affine(const Affine<F>& p) {
+        if (p.is_inf()) return inf();
+        F U = p.y.dbl();
+        F V = U.sqr();
+        F W = U * V;
+        F S = p.x * V;
+        F M = p.x.sqr();
+        M = M.dbl() + M;
+        F X3 = M.sqr() - S.dbl();
+        F Y3 = M * (S - X3) - W * p.y;
+        return {X3, Y3, V, W};
+    }
+    // madd-2008-s: 8M + 2S
+    MP_DEV XYZZ add_mixed(const Affine<F>& p) const {
+        if (p.is_inf()) return *this;
+        if (is_inf()) return {p.x, p.y, F::one(), F::one()};
+        F U2 = p.x * ZZ;
+        F S2 = p.y * ZZZ;
+        F P = U2 - X;
+        F R = S2 - Y;
+        if (P.is_zero()) {
+            if (R.is_zero()) return dbl_affine(p);
+            return inf();
+        }
+        F PP = P.sqr();
+        F PPP = P * PP;
+        F Q = X * PP;
+        F X3 = R.sqr() - PPP - Q.dbl();
+        F Y3 = R * (Q - X3) - Y * PPP;
+        return {X3, Y3, ZZ * PP, ZZZ * PPP};
+    }
+    MP_COLD XYZZ add_mixed_cold(const Affine<F>& p) const { return add_mixed(p); }
+    // add-2008-s: 12M + 2S
+    MP_COLD XYZZ add(const XYZZ& o) const {
+        if (o.is_inf()) return *this;
+        if (is_inf()) return o;
+        F U1 = X * o.ZZ;
+        F U2 = o.X * ZZ;
+        F S1 = Y * o.ZZZ;
+        F S2 = o.Y * ZZZ;
+        F P = U2 - U1;
+        F R = S2 - S1;
+        if (P.is_zero()) {
+            if (R.is_zero()) return dbl();
+            return inf();
+        }
+        F PP = P.sqr();
+        F PPP = P * PP;
+        F Q = U1 * PP;
+        F X3 = R.sqr() - PPP - Q.dbl();
+        F Y3 = R * (Q - X3) - S1 * PPP;
+        return {X3, Y3, ZZ * o.ZZ * PP, ZZZ * o.ZZZ * PPP};
+    }
+    // x = X/ZZ, y = Y/ZZZ with one inversion: i = (ZZ*ZZZ)^-1, 1/ZZ = i*ZZZ, 1/ZZZ = i*ZZ
+    MP_COLD Affine<F> to_affine() const {
+        if (is_inf()) return Affine<F>::inf();
+        F i = (ZZ * ZZZ).inv();
+        return {X * (i * ZZZ), Y * (i * ZZ)};
+    }
+};
+
+using G1Affine = Affine<Fq>;
+using G2Affine = Affine<Fq2>;
+using G1XYZZ = XYZZ<Fq>;
+using G2XYZZ = XYZZ<Fq2>;
+
+}  // namespace mp

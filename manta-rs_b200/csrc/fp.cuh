@@ -1,0 +1,294 @@
+// Montgomery prime-field arithmetic on the sm_100a integer pipe (32-bit limbs, little-endian).
+//
+// Replaces, on the device, ark-ff 0.3 `Fp256`/`Fp384` (the arithmetic under
+// manta-crypto/src/arkworks/ff.rs:24-75; upstream crate un-vendored).
+// Field elements are kept in Montgomery form (value * R mod p, R = 2^(32 N)) and fully reduced
+// (< p) between operations, so equality and the final canonical conversion are plain limb compares.
+//
+// Multiply: operand-scanning CIOS with the accumulator split into an "even-position" and an
+// "odd-position" limb array, so that every 32x32->64 product is added by one carry-chained
+// mad.lo.cc/madc.hi.cc pair — ptxas fuses each pair into a single IMAD.WIDE.U32(.X) with the carry
+// in a predicate.  Cost per product: 2 N^2 wide MACs + N low multiplies (N = 12: 300; N = 8: 136).
+#pragma once
+#include <cstdint>
+#include "bls12_381_constants.cuh"
+
+#define MP_DEV __device__ __forceinline__
+// out-of-line device code for everything off the hot loops (keeps cicc/ptxas time and code size sane)
+#define MP_COLD __device__ __noinline__
+
+namespace mp {
+
+// ---- carry-chain primitives (PTX condition-code register; keep statements adjacent) ----------
+MP_DEV void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    asm volatile("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+// (lo,hi) += a*b            -> CC
+MP_DEV void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+// (lo,hi) += a*b + CC       -> CC
+MP_DEV void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+// (lo,hi) = a*b + (clo,chi) + CC -> CC
+MP_DEV void madc_wide_cc_from(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b), "r"(clo), "r"(chi));
+}
+// (lo,hi) = a*b + CC  (top pair of a shifted chain; cannot carry out)
+MP_DEV void madc_wide_top(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.u32 %1, %2, %3, 0;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+MP_DEV void add_cc(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+MP_DEV void addc_cc(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+MP_DEV void addc(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+MP_DEV void sub_cc(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+MP_DEV void subc_cc(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+MP_DEV void subc(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+
+// ---- field parameter packs ---------------------------------------------------------------------
+struct FqParams {
+    static constexpr int N = 12;
+    static constexpr uint32_t M0 = FQ_M0;
+    static constexpr int BITS = 381;
+    MP_DEV static const uint32_t* mod() { return FQ_MOD; }
+    MP_DEV static const uint32_t* one() { return FQ_ONE; }
+    MP_DEV static const uint32_t* r2() { return FQ_R2; }
+    MP_DEV static const uint32_t* pm2() { return FQ_PM2; }
+    MP_DEV static const uint32_t* half() { return FQ_HALF; }
+};
+struct FrParams {
+    static constexpr int N = 8;
+    static constexpr uint32_t M0 = FR_M0;
+    static constexpr int BITS = 255;
+    MP_DEV static const uint32_t* mod() { return FR_MOD; }
+    MP_DEV static const uint32_t* one() { return FR_ONE; }
+    MP_DEV static const uint32_t* r2() { return FR_R2; }
+    MP_DEV static const uint32_t* pm2() { return FR_PM2; }
+    MP_DEV static const uint32_t* half() { return FR_HALF; }
+};
+
+template <class P>
+struct Fp {
+    static constexpr int N = P::N;
+    uint32_t l[N];
+
+    // ---- constructors -------------------------------------------------------------------------
+    MP_DEV static Fp zero() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = 0;
+        return r;
+    }
+    MP_DEV static Fp one() { return from_const(P::one()); }
+    MP_DEV static Fp from_const(const uint32_t* c) {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = c[i];
+        return r;
+    }
+    // 16-byte vector loads/stores (pointers must be 16-byte aligned)
+    MP_DEV static Fp load(const void* p) {
+        Fp r;
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+        for (int i = 0; i < N / 4; i++) {
+            uint4 v = q[i];
+            r.l[4 * i] = v.x; r.l[4 * i + 1] = v.y; r.l[4 * i + 2] = v.z; r.l[4 * i + 3] = v.w;
+        }
+        return r;
+    }
+    MP_DEV static Fp load_ro(const void* p) {  // read-only path
+        Fp r;
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+        for (int i = 0; i < N / 4; i++) {
+            uint4 v = __ldg(q + i);
+            r.l[4 * i] = v.x; r.l[4 * i + 1] = v.y; r.l[4 * i + 2] = v.z; r.l[4 * i + 3] = v.w;
+        }
+        return r;
+    }
+    MP_DEV void store(void* p) const {
+        uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+        for (int i = 0; i < N / 4; i++) q[i] = make_uint4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
+    }
+
+    // ---- predicates ---------------------------------------------------------------------------
+    MP_DEV bool is_zero() const {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) acc |= l[i];
+        return acc == 0;
+    }
+    MP_DEV bool operator==(const Fp& o) const {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) acc |= l[i] ^ o.l[i];
+        return acc == 0;
+    }
+    MP_DEV bool operator!=(const Fp& o) const { return !(*this == o); }
+
+    // ---- raw multi-limb helpers -----------------------------------------------------------------
+    // r = a - b, returns borrow (1 if a < b)
+    MP_DEV static uint32_t sub_raw(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+        sub_cc(r[0], a[0], b[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) subc_cc(r[i], a[i], b[i]);
+        uint32_t borrow;
+        subc(borrow, 0, 0);
+        return borrow;  // 0 or 0xffffffff
+    }
+    // conditional final subtraction: x in [0, 2p) -> [0, p)
+    MP_DEV void reduce_once() {
+        uint32_t t[N];
+        const uint32_t* m = P::mod();
+        uint32_t borrow = sub_raw(t, l, m);
+#pragma unroll
+        for (int i = 0; i < N; i++) l[i] = borrow ? l[i] : t[i];
+    }
+
+    // ---- additive group -------------------------------------------------------------------------
+    MP_DEV Fp operator+(const Fp& o) const {
+        Fp r;
+        add_cc(r.l[0], l[0], o.l[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) addc_cc(r.l[i], l[i], o.l[i]);
+        addc(r.l[N - 1], l[N - 1], o.l[N - 1]);  // 2p < 2^(32N): no carry out
+        r.reduce_once();
+        return r;
+    }
+    MP_DEV Fp operator-(const Fp& o) const {
+        Fp r;
+        uint32_t borrow = sub_raw(r.l, l, o.l);
+        const uint32_t* m = P::mod();
+        uint32_t t[N];
+        add_cc(t[0], r.l[0], m[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) addc_cc(t[i], r.l[i], m[i]);
+        addc(t[N - 1], r.l[N - 1], m[N - 1]);
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = borrow ? t[i] : r.l[i];
+        return r;
+    }
+    MP_DEV Fp neg() const {
+        Fp r;
+        const uint32_t* m = P::mod();
+        sub_raw(r.l, m, l);
+        bool z = is_zero();
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = z ? 0u : r.l[i];
+        return r;
+    }
+    MP_DEV Fp dbl() const { return *this + *this; }
+    MP_DEV static Fp select(bool c, const Fp& a, const Fp& b) {  // c ? a : b
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = c ? a.l[i] : b.l[i];
+        return r;
+    }
+
+    // ---- Montgomery multiplication ----------------------------------------------------------------
+    // One CIOS row on the split accumulator.  `x` lives at even limb positions (x[0] = position 0),
+    // `y` at odd positions (y[k] = position k + 1).  Adds v * c where v has N limbs.
+    //   y-chain first (cannot carry out), then x-chain whose carry lands in y[N-1].
+    MP_DEV static void row_add(uint32_t* x, uint32_t* y, const uint32_t* v, uint32_t c) {
+        mad_wide_cc(y[0], y[1], v[1], c);
+#pragma unroll
+        for (int j = 3; j < N; j += 2) madc_wide_cc(y[j - 1], y[j], v[j], c);
+        // y chain never carries out of position N (bound argument in DESIGN.md); the CC it leaves is
+        // overwritten by the next chain start.
+        mad_wide_cc(x[0], x[1], v[0], c);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) madc_wide_cc(x[j], x[j + 1], v[j], c);
+        addc(y[N - 1], y[N - 1], 0);
+    }
+
+    MP_DEV Fp operator*(const Fp& o) const {
+        const uint32_t* m = P::mod();
+        // two role-swapping accumulators; after each row the value is divided by 2^32, which turns the
+        // odd-position array into the even-position one and shifts the other by two limbs.
+        uint32_t u[N], w[N];
+        // ---- row 0: plain products ----
+#pragma unroll
+        for (int j = 0; j < N; j += 2) {
+            mul_wide(u[j], u[j + 1], l[j], o.l[0]);      // even positions
+            mul_wide(w[j], w[j + 1], l[j + 1], o.l[0]);  // odd positions
+        }
+        {
+            uint32_t mi = u[0] * P::M0;
+            row_add(u, w, m, mi);
+        }
+        // now u[0] == 0 and the pending shift makes w the even-position array.
+#pragma unroll
+        for (int i = 1; i < N; i++) {
+            uint32_t* x = (i & 1) ? w : u;   // becomes even-position array
+            uint32_t* yo = (i & 1) ? u : w;  // old even array: yo[0] == 0, yo[1] folds into x[0], rest shifts by 2
+            uint32_t bi = o.l[i];
+            // fold + shifted y-chain:  y'[k] = yo[k + 2]
+            add_cc(x[0], x[0], yo[1]);
+#pragma unroll
+            for (int j = 1; j < N - 1; j += 2) madc_wide_cc_from(yo[j - 1], yo[j], l[j], bi, yo[j + 1], yo[j + 2]);
+            madc_wide_top(yo[N - 2], yo[N - 1], l[N - 1], bi);
+            // x-chain
+            mad_wide_cc(x[0], x[1], l[0], bi);
+#pragma unroll
+            for (int j = 2; j < N; j += 2) madc_wide_cc(x[j], x[j + 1], l[j], bi);
+            addc(yo[N - 1], yo[N - 1], 0);
+            uint32_t mi = x[0] * P::M0;
+            row_add(x, yo, m, mi);
+        }
+        // merge: result[k] = y'[k] + x[k + 1]
+        uint32_t* x = ((N - 1) & 1) ? w : u;  // even-position array of the last row (x[0] == 0)
+        uint32_t* y = ((N - 1) & 1) ? u : w;
+        Fp r;
+        add_cc(r.l[0], y[0], x[1]);
+#pragma unroll
+        for (int k = 1; k < N - 1; k++) addc_cc(r.l[k], y[k], x[k + 1]);
+        addc(r.l[N - 1], y[N - 1], 0);
+        r.reduce_once();
+        return r;
+    }
+    MP_DEV Fp sqr() const { return *this * *this; }
+
+    // ---- conversions ------------------------------------------------------------------------------
+    MP_COLD Fp mul_cold(const Fp& o) const { return *this * o; }
+    MP_DEV Fp to_mont() const { return *this * from_const(P::r2()); }
+    MP_DEV Fp from_mont() const {
+        Fp o = zero();
+        o.l[0] = 1;
+        return *this * o;
+    }
+
+    // ---- exponentiation / inversion (Fermat; off the hot loop) ----------------------------------------
+    MP_COLD Fp pow_const(const uint32_t* e, int bits) const {
+        Fp r = one();
+        for (int i = bits - 1; i >= 0; i--) {
+            r = r.sqr();
+            if ((e[i >> 5] >> (i & 31)) & 1) r = r * *this;
+        }
+        return r;
+    }
+    MP_COLD Fp pow_u64(uint64_t e) const {
+        Fp r = one();
+        for (int i = 63; i >= 0; i--) {
+            r = r.sqr();
+            if ((e >> i) & 1) r = r * *this;
+        }
+        return r;
+    }
+    MP_DEV Fp inv() const { return pow_const(P::pm2(), P::BITS); }  // 0 -> 0
+
+    // canonical (non-Montgomery) integer > (p-1)/2 ?   (ark's `y > -y` flag)
+    MP_DEV static bool canonical_gt_half(const Fp& canon) {
+        uint32_t t[N];
+        const uint32_t* h = P::half();
+        uint32_t borrow = sub_raw(t, h, canon.l);  // half - canon < 0  <=> canon > half
+        return borrow != 0;
+    }
+};
+
+using Fq = Fp<FqParams>;
+using Fr = Fp<FrParams>;
+
+}  // namespace mp

@@ -1,0 +1,581 @@
+// Bucket-method multi-scalar multiplication on sm_100a (see msm.cuh for the pipeline).
+//
+// Replaces ark-ec 0.3 `VariableBaseMSM::multi_scalar_mul` — the five calls inside ark-groth16's
+// `create_proof` behind manta-crypto/src/arkworks/groth16.rs:597 and the direct benchmark use at
+// manta-benchmark/src/ecc.rs:62-118.  Only the affine value of the result is observable,
+// so signed digits, precomputed window tables and XYZZ buckets give bit-identical outputs.
+#include <vector>
+
+#include "msm.cuh"
+
+namespace mp {
+
+// ---------------------------------------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------------------------------------
+MsmGeom msm_geom(int c, int groups, uint32_t n_scalars, uint32_t table_stride) {
+    MsmGeom g{};
+    g.c = c;
+    g.windows = 255 / c + 1;
+    if (groups <= 0 || groups > g.windows) groups = g.windows;
+    g.groups = groups;
+    g.rows = (g.windows + groups - 1) / groups;
+    g.n_scalars = n_scalars;
+    g.table_stride = table_stride;
+    g.bpg = 1u << (c - 1);
+    g.n_buckets = g.bpg * groups;
+    g.max_entries = n_scalars * (uint32_t)g.windows;
+    g.max_items = g.n_buckets + g.max_entries / MSM_SEG + 1;
+    uint32_t l1pg = (g.bpg + MSM_RED_S1 - 1) / MSM_RED_S1;
+    uint32_t l2pg = (l1pg + MSM_RED_S2 - 1) / MSM_RED_S2;
+    g.l1_chunks = l1pg * groups;
+    g.l2_chunks = l2pg * groups;
+    return g;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+size_t MsmSortWs::bytes(const MsmGeom& g, size_t batch) const {
+    size_t b = 0;
+    b += align256(batch * g.n_buckets * 4) * 3;          // cnt, start, fill
+    b += align256(batch * (g.n_buckets + 1) * 4);        // slot_base
+    b += align256(batch * (size_t)g.max_items * 8);      // items
+    b += align256(batch * 4);                            // n_items
+    b += align256(batch * (size_t)g.max_entries * 4);    // entries
+    return b;
+}
+
+int msm_sort_ws_alloc(MsmSortWs& ws, const MsmGeom& g, size_t batch, DevBuf& backing) {
+    MP_TRY(backing.alloc(ws.bytes(g, batch)));
+    char* p = backing.as<char>();
+    auto take = [&](size_t n) { char* r = p; p += align256(n); return r; };
+    ws.cnt = (uint32_t*)take(batch * g.n_buckets * 4);
+    ws.start = (uint32_t*)take(batch * g.n_buckets * 4);
+    ws.fill = (uint32_t*)take(batch * g.n_buckets * 4);
+    ws.slot_base = (uint32_t*)take(batch * (g.n_buckets + 1) * 4);
+    ws.items = (uint32_t*)take(batch * (size_t)g.max_items * 8);
+    ws.n_items = (uint32_t*)take(batch * 4);
+    ws.entries = (uint32_t*)take(batch * (size_t)g.max_entries * 4);
+    return MP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// signed-digit recoding
+// ---------------------------------------------------------------------------------------------------------
+// bits [pos, pos + c) of a 256-bit little-endian integer (c <= 16)
+MP_DEV uint32_t scalar_bits(const uint32_t* s, int pos, int c) {
+    int w = pos >> 5, o = pos & 31;
+    uint64_t v = s[w];
+    if (w + 1 < 8) v |= (uint64_t)s[w + 1] << 32;
+    return (uint32_t)(v >> o) & ((1u << c) - 1);
+}
+
+// Calls f(window, bucket_in_group (0-based), negative) for every non-zero digit.
+template <class Fn>
+MP_DEV void for_each_digit(const uint32_t* s, int c, int windows, Fn f) {
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (c - 1);
+    for (int w = 0; w < windows; w++) {
+        uint32_t raw = scalar_bits(s, w * c, c) + carry;
+        bool neg = raw > half;
+        uint32_t mag = neg ? (1u << c) - raw : raw;
+        carry = neg ? 1u : 0u;
+        if (mag) f(w, mag - 1, neg);
+    }
+}
+
+__global__ void k_msm_hist(MsmGeom g, const uint32_t* __restrict__ scalars, size_t stride_words, uint32_t* cnt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t b = blockIdx.y;
+    if (i >= g.n_scalars) return;
+    uint32_t s[8];
+    const uint4* p = reinterpret_cast<const uint4*>(scalars + b * stride_words + (size_t)i * 8);
+    uint4 lo = __ldg(p), hi = __ldg(p + 1);
+    s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+    uint32_t* my = cnt + (size_t)b * g.n_buckets;
+    for_each_digit(s, g.c, g.windows, [&](int w, uint32_t bk, bool) {
+        uint32_t grp = w % g.groups;
+        atomicAdd(&my[grp * g.bpg + bk], 1u);
+    });
+}
+
+__global__ void k_msm_scatter(MsmGeom g, const uint32_t* __restrict__ scalars, size_t stride_words,
+                              const uint32_t* __restrict__ start, uint32_t* fill, uint32_t* entries) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t b = blockIdx.y;
+    if (i >= g.n_scalars) return;
+    uint32_t s[8];
+    const uint4* p = reinterpret_cast<const uint4*>(scalars + b * stride_words + (size_t)i * 8);
+    uint4 lo = __ldg(p), hi = __ldg(p + 1);
+    s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+    const uint32_t* st = start + (size_t)b * g.n_buckets;
+    uint32_t* fl = fill + (size_t)b * g.n_buckets;
+    uint32_t* en = entries + (size_t)b * g.max_entries;
+    for_each_digit(s, g.c, g.windows, [&](int w, uint32_t bk, bool neg) {
+        uint32_t grp = w % g.groups, row = w / g.groups;
+        uint32_t k = grp * g.bpg + bk;
+        uint32_t pos = st[k] + atomicAdd(&fl[k], 1u);
+        en[pos] = (neg ? 0x80000000u : 0u) | (row * g.table_stride + i);
+    });
+}
+
+// One block per batch element: prefix sums over bucket counts (entry offsets and partial-sum slots) and the
+// work-item list ordered by descending segment length, so that the lanes of a warp run equally long loops.
+constexpr int PLAN_THREADS = 1024;
+__global__ void __launch_bounds__(PLAN_THREADS) k_msm_plan(MsmGeom g, const uint32_t* __restrict__ cnt, uint32_t* start,
+                                                          uint32_t* slot_base, uint2* items, uint32_t* n_items) {
+    __shared__ uint32_t sh_e[PLAN_THREADS], sh_s[PLAN_THREADS];
+    __shared__ uint32_t cls[MSM_SEG + 1];
+    const uint32_t b = blockIdx.x, tid = threadIdx.x;
+    const uint32_t* c = cnt + (size_t)b * g.n_buckets;
+    uint32_t* st = start + (size_t)b * g.n_buckets;
+    uint32_t* sb = slot_base + (size_t)b * (g.n_buckets + 1);
+    uint2* it = items + (size_t)b * g.max_items;
+    const uint32_t per = (g.n_buckets + PLAN_THREADS - 1) / PLAN_THREADS;
+    const uint32_t k0 = tid * per, k1 = min(k0 + per, g.n_buckets);
+    if (tid <= MSM_SEG) cls[tid] = 0;
+    uint32_t se = 0, ss = 0;
+    for (uint32_t k = k0; k < k1; k++) {
+        uint32_t v = c[k];
+        se += v;
+        ss += (v + MSM_SEG - 1) / MSM_SEG;
+    }
+    sh_e[tid] = se;
+    sh_s[tid] = ss;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the per-thread sums
+    for (int off = 1; off < PLAN_THREADS; off <<= 1) {
+        uint32_t ve = 0, vs = 0;
+        if (tid >= off) { ve = sh_e[tid - off]; vs = sh_s[tid - off]; }
+        __syncthreads();
+        sh_e[tid] += ve;
+        sh_s[tid] += vs;
+        __syncthreads();
+    }
+    uint32_t oe = sh_e[tid] - se, os = sh_s[tid] - ss;
+    for (uint32_t k = k0; k < k1; k++) {
+        uint32_t v = c[k];
+        st[k] = oe;
+        sb[k] = os;
+        oe += v;
+        uint32_t full = v / MSM_SEG, rem = v % MSM_SEG;
+        os += full + (rem ? 1 : 0);
+        if (full) atomicAdd(&cls[0], full);
+        if (rem) atomicAdd(&cls[MSM_SEG - rem], 1u);
+    }
+    if (tid == PLAN_THREADS - 1) {
+        sb[g.n_buckets] = sh_s[tid];
+        n_items[b] = sh_s[tid];
+    }
+    __syncthreads();
+    if (tid == 0) {  // exclusive scan over the length classes (class 0 = full segments first)
+        uint32_t run = 0;
+        for (int q = 0; q < MSM_SEG; q++) {
+            uint32_t v = cls[q];
+            cls[q] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = k0; k < k1; k++) {
+        uint32_t v = c[k];
+        uint32_t full = v / MSM_SEG, rem = v % MSM_SEG;
+        if (full) {
+            uint32_t pos = atomicAdd(&cls[0], full);
+            for (uint32_t sidx = 0; sidx < full; sidx++) it[pos + sidx] = make_uint2(k, sidx);
+        }
+        if (rem) {
+            uint32_t pos = atomicAdd(&cls[MSM_SEG - rem], 1u);
+            it[pos] = make_uint2(k, full);
+        }
+    }
+}
+
+int msm_sort(const MsmGeom& g, const uint32_t* scalars, size_t stride_words, size_t batch, const MsmSortWs& ws,
+             cudaStream_t st) {
+    if (batch == 0 || g.n_scalars == 0) return MP_OK;
+    MP_CUDA_TRY(cudaMemsetAsync(ws.cnt, 0, batch * g.n_buckets * 4, st));
+    MP_CUDA_TRY(cudaMemsetAsync(ws.fill, 0, batch * g.n_buckets * 4, st));
+    dim3 grid(div_up(g.n_scalars, 256), (unsigned)batch);
+    k_msm_hist<<<grid, 256, 0, st>>>(g, scalars, stride_words, ws.cnt);
+    MP_KERNEL_CHECK();
+    k_msm_plan<<<(unsigned)batch, PLAN_THREADS, 0, st>>>(g, ws.cnt, ws.start, ws.slot_base, (uint2*)ws.items, ws.n_items);
+    MP_KERNEL_CHECK();
+    k_msm_scatter<<<grid, 256, 0, st>>>(g, scalars, stride_words, ws.start, ws.fill, ws.entries);
+    MP_KERNEL_CHECK();
+    return MP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// bucket accumulation: one thread per work item (a bucket, or a <= MSM_SEG slice of a large bucket)
+// ---------------------------------------------------------------------------------------------------------
+struct AccArgs {
+    const void* table[4];
+    void* partial[4];
+};
+
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_msm_accumulate(MsmGeom g, AccArgs a, const uint32_t* __restrict__ cnt,
+                                                           const uint32_t* __restrict__ start,
+                                                           const uint32_t* __restrict__ slot_base,
+                                                           const uint2* __restrict__ items,
+                                                           const uint32_t* __restrict__ n_items,
+                                                           const uint32_t* __restrict__ entries) {
+    const uint32_t b = blockIdx.y, m = blockIdx.z;
+    const uint32_t j = blockIdx.x * THREADS + threadIdx.x;
+    if (j >= n_items[b]) return;
+    const uint2 item = items[(size_t)b * g.max_items + j];
+    const uint32_t k = item.x, seg = item.y;
+    const uint32_t total = cnt[(size_t)b * g.n_buckets + k];
+    const uint32_t len = min((uint32_t)MSM_SEG, total - seg * MSM_SEG);
+    const uint32_t* en = entries + (size_t)b * g.max_entries + start[(size_t)b * g.n_buckets + k] + seg * MSM_SEG;
+    const uint32_t slot = slot_base[(size_t)b * (g.n_buckets + 1) + k] + seg;
+    const uint32_t* tab = reinterpret_cast<const uint32_t*>(a.table[m]);
+    constexpr int AW = Affine<F>::WORDS;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t e = 0; e < len; e++) {
+        uint32_t idx = __ldg(en + e);
+        Affine<F> p = Affine<F>::load_ro(tab + (size_t)(idx & 0x7fffffffu) * AW);
+        if (idx >> 31) p.y = p.y.neg();
+        acc = acc.add_mixed(p);
+    }
+    uint32_t* out = reinterpret_cast<uint32_t*>(a.partial[m]) + ((size_t)b * g.max_items + slot) * XYZZ<F>::WORDS;
+    acc.store(out);
+}
+
+template <class F>
+static int accumulate_impl(const MsmGeom& g, const MsmSortWs& ws, const MsmTables& t, size_t batch, cudaStream_t st) {
+    if (batch == 0 || t.n_msm == 0) return MP_OK;
+    AccArgs a{};
+    for (int i = 0; i < t.n_msm; i++) { a.table[i] = t.table[i]; a.partial[i] = t.partial[i]; }
+    constexpr int THREADS = 128;
+    dim3 grid(div_up(g.max_items, THREADS), (unsigned)batch, (unsigned)t.n_msm);
+    k_msm_accumulate<F, THREADS><<<grid, THREADS, 0, st>>>(g, a, ws.cnt, ws.start, ws.slot_base, (const uint2*)ws.items,
+                                                          ws.n_items, ws.entries);
+    MP_KERNEL_CHECK();
+    return MP_OK;
+}
+int msm_accumulate_g1(const MsmGeom& g, const MsmSortWs& ws, const MsmTables& t, size_t batch, cudaStream_t st) {
+    return accumulate_impl<Fq>(g, ws, t, batch, st);
+}
+int msm_accumulate_g2(const MsmGeom& g, const MsmSortWs& ws, const MsmTables& t, size_t batch, cudaStream_t st) {
+    return accumulate_impl<Fq2>(g, ws, t, batch, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// bucket reduction  sum_k k * B_k  per window group, three levels of running sums
+// ---------------------------------------------------------------------------------------------------------
+struct RedArgs {
+    const void* partial[4];
+    void* result[4];
+    void* scratch;  // [n_msm][batch][l1_chunks + l2_chunks][3] XYZZ
+};
+
+template <class F>
+MP_DEV XYZZ<F>* red_scratch(const MsmGeom& g, void* scratch, uint32_t m, uint32_t b, uint32_t batch) {
+    size_t per = (size_t)(g.l1_chunks + g.l2_chunks) * 3;
+    return reinterpret_cast<XYZZ<F>*>(scratch) + ((size_t)m * batch + b) * per;
+}
+
+// level 1: thread = chunk of MSM_RED_S1 buckets -> (s = sum B, a = sum (j+1) B)
+template <class F>
+__global__ void __launch_bounds__(64) k_msm_reduce1(MsmGeom g, RedArgs a, const uint32_t* __restrict__ slot_base, uint32_t batch) {
+    const uint32_t l1pg = g.l1_chunks / g.groups;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // chunk within all groups
+    const uint32_t b = blockIdx.y, m = blockIdx.z;
+    if (t >= g.l1_chunks) return;
+    const uint32_t grp = t / l1pg, tl = t % l1pg;
+    const uint32_t* sb = slot_base + (size_t)b * (g.n_buckets + 1);
+    const XYZZ<F>* part = reinterpret_cast<const XYZZ<F>*>(a.partial[m]) + (size_t)b * g.max_items;
+    XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
+    for (int j = MSM_RED_S1 - 1; j >= 0; j--) {
+        uint32_t kl = tl * MSM_RED_S1 + j;
+        if (kl < g.bpg) {
+            uint32_t k = grp * g.bpg + kl;
+            uint32_t s0 = sb[k], s1 = sb[k + 1];
+            for (uint32_t s = s0; s < s1; s++) run = run.add(XYZZ<F>::load(part + s));
+        }
+        acc = acc.add(run);
+    }
+    XYZZ<F>* sc = red_scratch<F>(g, a.scratch, m, b, batch);
+    run.store(sc + (size_t)t * 3);
+    acc.store(sc + (size_t)t * 3 + 1);
+}
+
+// level 2: thread = MSM_RED_S2 level-1 chunks -> (rs = sum s, ww = sum (q+1) s, va = sum a)
+template <class F>
+__global__ void __launch_bounds__(32) k_msm_reduce2(MsmGeom g, RedArgs a, uint32_t batch) {
+    const uint32_t l1pg = g.l1_chunks / g.groups, l2pg = g.l2_chunks / g.groups;
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t b = blockIdx.y, m = blockIdx.z;
+    if (u >= g.l2_chunks) return;
+    const uint32_t grp = u / l2pg, ul = u % l2pg;
+    XYZZ<F>* sc = red_scratch<F>(g, a.scratch, m, b, batch);
+    XYZZ<F> rs = XYZZ<F>::inf(), ww = XYZZ<F>::inf(), va = XYZZ<F>::inf();
+    for (int q = MSM_RED_S2 - 1; q >= 0; q--) {
+        uint32_t tl = ul * MSM_RED_S2 + q;
+        if (tl < l1pg) {
+            size_t t = (size_t)grp * l1pg + tl;
+            rs = rs.add(XYZZ<F>::load(sc + t * 3));
+            va = va.add(XYZZ<F>::load(sc + t * 3 + 1));
+        }
+        ww = ww.add(rs);
+    }
+    XYZZ<F>* o = sc + (size_t)g.l1_chunks * 3 + (size_t)u * 3;
+    rs.store(o);
+    ww.store(o + 1);
+    va.store(o + 2);
+}
+
+template <class F>
+MP_DEV XYZZ<F> dbl_n(XYZZ<F> p, int n) {
+    for (int i = 0; i < n; i++) p = p.dbl();
+    return p;
+}
+
+// level 3: one thread per (msm, batch, group)
+template <class F>
+__global__ void __launch_bounds__(32) k_msm_reduce3(MsmGeom g, RedArgs a, uint32_t batch) {
+    const uint32_t l2pg = g.l2_chunks / g.groups;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;  // over batch * groups
+    const uint32_t m = blockIdx.y;
+    if (idx >= batch * g.groups) return;
+    const uint32_t b = idx / g.groups, grp = idx % g.groups;
+    XYZZ<F>* sc = red_scratch<F>(g, a.scratch, m, b, batch) + (size_t)g.l1_chunks * 3 + (size_t)grp * l2pg * 3;
+    XYZZ<F> R = XYZZ<F>::inf(), Wu = XYZZ<F>::inf(), WW = XYZZ<F>::inf(), VA = XYZZ<F>::inf();
+    for (int u = (int)l2pg - 1; u >= 0; u--) {
+        R = R.add(XYZZ<F>::load(sc + (size_t)u * 3));
+        Wu = Wu.add(R);
+        WW = WW.add(XYZZ<F>::load(sc + (size_t)u * 3 + 1));
+        VA = VA.add(XYZZ<F>::load(sc + (size_t)u * 3 + 2));
+    }
+    // sum_t t*s_t = S2*Wu + WW - (S2+1)*R ;  total = VA + S1 * that
+    int l2 = 0, l1 = 0;
+    while ((1 << l2) < MSM_RED_S2) l2++;
+    while ((1 << l1) < MSM_RED_S1) l1++;
+    XYZZ<F> T = dbl_n(Wu, l2).add(WW);
+    XYZZ<F> sub = dbl_n(R, l2).add(R);
+    T = T.add(sub.neg());
+    T = dbl_n(T, l1).add(VA);
+    T.store(reinterpret_cast<XYZZ<F>*>(a.result[m]) + (size_t)b * g.groups + grp);
+}
+
+size_t msm_reduce_scratch_bytes(const MsmGeom& g, size_t batch, int n_msm, bool g2) {
+    size_t words = g2 ? XYZZ<Fq2>::WORDS : XYZZ<Fq>::WORDS;
+    return (size_t)n_msm * batch * (g.l1_chunks + g.l2_chunks) * 3 * words * 4;
+}
+
+template <class F>
+static int reduce_impl(const MsmGeom& g, const MsmSortWs& ws, const MsmTables& t, size_t batch, void* scratch, cudaStream_t st) {
+    if (batch == 0 || t.n_msm == 0) return MP_OK;
+    RedArgs a{};
+    for (int i = 0; i < t.n_msm; i++) { a.partial[i] = t.partial[i]; a.result[i] = t.result[i]; }
+    a.scratch = scratch;
+    k_msm_reduce1<F><<<dim3(div_up(g.l1_chunks, 64), (unsigned)batch, (unsigned)t.n_msm), 64, 0, st>>>(g, a, ws.slot_base, (uint32_t)batch);
+    MP_KERNEL_CHECK();
+    k_msm_reduce2<F><<<dim3(div_up(g.l2_chunks, 32), (unsigned)batch, (unsigned)t.n_msm), 32, 0, st>>>(g, a, (uint32_t)batch);
+    MP_KERNEL_CHECK();
+    k_msm_reduce3<F><<<dim3(div_up(batch * g.groups, 32), (unsigned)t.n_msm), 32, 0, st>>>(g, a, (uint32_t)batch);
+    MP_KERNEL_CHECK();
+    return MP_OK;
+}
+int msm_reduce_g1(const MsmGeom& g, const MsmSortWs& ws, const MsmTables& t, size_t batch, void* scratch, cudaStream_t st) {
+    return reduce_impl<Fq>(g, ws, t, batch, scratch, st);
+}
+int msm_reduce_g2(const MsmGeom& g, const MsmSortWs& ws, const MsmTables& t, size_t batch, void* scratch, cudaStream_t st) {
+    return reduce_impl<Fq2>(g, ws, t, batch, scratch, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tables and Horner
+// ---------------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(64) k_msm_build_table(MsmGeom g, const uint32_t* __restrict__ bases, uint32_t n, uint32_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.table_stride) return;
+    constexpr int AW = Affine<F>::WORDS;
+    Affine<F> p = (i < n) ? Affine<F>::load(bases + (size_t)i * AW) : Affine<F>::inf();
+    for (int t = 0; t < g.rows; t++) {
+        p.store(out + ((size_t)t * g.table_stride + i) * AW);
+        if (t + 1 < g.rows && !p.is_inf()) {
+            XYZZ<F> q = XYZZ<F>::dbl_affine(p);
+            q = dbl_n(q, g.c * g.groups - 1);
+            p = q.to_affine();
+        }
+    }
+}
+
+template <class F>
+__global__ void __launch_bounds__(32) k_msm_horner(MsmGeom g, const XYZZ<F>* __restrict__ res, XYZZ<F>* out, uint32_t count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const XYZZ<F>* r = res + (size_t)i * g.groups;
+    XYZZ<F> acc = XYZZ<F>::load(r + g.groups - 1);
+    for (int grp = g.groups - 2; grp >= 0; grp--) acc = dbl_n(acc, g.c).add(XYZZ<F>::load(r + grp));
+    acc.store(out + i);
+}
+
+int msm_build_table_g1(const MsmGeom& g, const void* bases, uint32_t n, void* out, cudaStream_t st) {
+    k_msm_build_table<Fq><<<div_up(g.table_stride, 64), 64, 0, st>>>(g, (const uint32_t*)bases, n, (uint32_t*)out);
+    MP_KERNEL_CHECK();
+    return MP_OK;
+}
+int msm_build_table_g2(const MsmGeom& g, const void* bases, uint32_t n, void* out, cudaStream_t st) {
+    k_msm_build_table<Fq2><<<div_up(g.table_stride, 64), 64, 0, st>>>(g, (const uint32_t*)bases, n, (uint32_t*)out);
+    MP_KERNEL_CHECK();
+    return MP_OK;
+}
+int msm_horner_g1(const MsmGeom& g, const void* res, void* out, size_t count, cudaStream_t st) {
+    k_msm_horner<Fq><<<div_up(count, 32), 32, 0, st>>>(g, (const XYZZ<Fq>*)res, (XYZZ<Fq>*)out, (uint32_t)count);
+    MP_KERNEL_CHECK();
+    return MP_OK;
+}
+int msm_horner_g2(const MsmGeom& g, const void* res, void* out, size_t count, cudaStream_t st) {
+    k_msm_horner<Fq2><<<div_up(count, 32), 32, 0, st>>>(g, (const XYZZ<Fq2>*)res, (XYZZ<Fq2>*)out, (uint32_t)count);
+    MP_KERNEL_CHECK();
+    return MP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stand-alone MSM over caller-supplied bases (no precomputed rows: one bucket set per window + Horner)
+// ---------------------------------------------------------------------------------------------------------
+template <class F> __global__ void k_xyzz_to_affine(const XYZZ<F>* in, Affine<F>* out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) XYZZ<F>::load(in + i).to_affine().store(out + i);
+}
+
+static int pick_window(size_t n) {
+    // balance n*W mixed adds against 2*W*2^(c-1) reduction adds (each ~1.4 mixed adds)
+    int best = 4;
+    double best_cost = 1e300;
+    for (int c = 4; c <= 16; c++) {
+        int w = 255 / c + 1;
+        double cost = (double)n * w + 2.8 * w * (double)(1u << (c - 1));
+        if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    return best;
+}
+
+template <class F>
+static int msm_standalone(int device, const uint8_t* bases, const uint64_t* scalars, size_t n, uint8_t* out_point, float* out_ms) {
+    constexpr bool G2 = (FieldWords<F>::W == 24);
+    const size_t pb = G2 ? MP_G2_BYTES : MP_G1_BYTES;
+    if (!out_point || (n && (!bases || !scalars))) return MP_ERR_INVALID_ARG;
+    if (n > (1u << 26)) { set_error_detail("msm: n = %zu exceeds 2^26", n); return MP_ERR_UNSUPPORTED; }
+    MP_TRY(use_device(device));
+    if (n == 0) {
+        memset(out_point, 0, pb);
+        out_point[pb - 1] = 0x40;
+        if (out_ms) *out_ms = 0;
+        return MP_OK;
+    }
+    MsmGeom g = msm_geom(pick_window(n), 0, (uint32_t)n, (uint32_t)n);
+    DevBuf d_bases, d_scalars, d_sort, d_partial, d_result, d_scratch, d_out;
+    MP_TRY(d_bases.alloc(n * pb));
+    MP_TRY(d_scalars.alloc(n * 32));
+    MsmSortWs ws;
+    MP_TRY(msm_sort_ws_alloc(ws, g, 1, d_sort));
+    MP_TRY(d_partial.alloc((size_t)g.max_items * XYZZ<F>::WORDS * 4));
+    MP_TRY(d_result.alloc((size_t)g.groups * XYZZ<F>::WORDS * 4));
+    MP_TRY(d_scratch.alloc(msm_reduce_scratch_bytes(g, 1, 1, G2)));
+    MP_TRY(d_out.alloc(XYZZ<F>::WORDS * 4 + pb));
+    MP_CUDA_TRY(cudaMemcpy(d_bases.p, bases, n * pb, cudaMemcpyHostToDevice));
+    MP_CUDA_TRY(cudaMemcpy(d_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice));
+    if (G2) MP_TRY(points_from_ark_g2(d_bases.p, d_bases.p, n, 0));
+    else MP_TRY(points_from_ark_g1(d_bases.p, d_bases.p, n, 0));
+    cudaEvent_t e0, e1;
+    MP_CUDA_TRY(cudaEventCreate(&e0));
+    MP_CUDA_TRY(cudaEventCreate(&e1));
+    MP_CUDA_TRY(cudaEventRecord(e0, 0));
+    MP_TRY(msm_sort(g, d_scalars.as<uint32_t>(), n * 8, 1, ws, 0));
+    MsmTables t{};
+    t.n_msm = 1;
+    t.table[0] = d_bases.p;
+    t.partial[0] = d_partial.p;
+    t.result[0] = d_result.p;
+    if (G2) {
+        MP_TRY(msm_accumulate_g2(g, ws, t, 1, 0));
+        MP_TRY(msm_reduce_g2(g, ws, t, 1, d_scratch.p, 0));
+        MP_TRY(msm_horner_g2(g, d_result.p, d_out.p, 1, 0));
+    } else {
+        MP_TRY(msm_accumulate_g1(g, ws, t, 1, 0));
+        MP_TRY(msm_reduce_g1(g, ws, t, 1, d_scratch.p, 0));
+        MP_TRY(msm_horner_g1(g, d_result.p, d_out.p, 1, 0));
+    }
+    MP_CUDA_TRY(cudaEventRecord(e1, 0));
+    char* aff = d_out.as<char>() + XYZZ<F>::WORDS * 4;
+    k_xyzz_to_affine<F><<<1, 1>>>((const XYZZ<F>*)d_out.p, (Affine<F>*)aff, 1);
+    MP_KERNEL_CHECK();
+    if (G2) MP_TRY(points_to_ark_g2(aff, aff, 1, 0));
+    else MP_TRY(points_to_ark_g1(aff, aff, 1, 0));
+    MP_CUDA_TRY(cudaMemcpy(out_point, aff, pb, cudaMemcpyDeviceToHost));
+    float ms = 0;
+    MP_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (out_ms) *out_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return MP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fixed-base helper (keygen): out[i] = k_i * G
+// ---------------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(64) k_fixed_base(const uint32_t* __restrict__ gen, const uint32_t* __restrict__ scalars,
+                                                  uint32_t* out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    constexpr int AW = Affine<F>::WORDS;
+    Affine<F> gpt = Affine<F>::load(gen);
+    const uint32_t* s = scalars + i * 8;
+    XYZZ<F> r = XYZZ<F>::inf();
+    for (int bit = 254; bit >= 0; bit--) {
+        r = r.dbl();
+        if ((s[bit >> 5] >> (bit & 31)) & 1) r = r.add_mixed_cold(gpt);
+    }
+    r.to_affine().store(out + i * AW);
+}
+
+__global__ void k_copy_gen(uint32_t* out, int which) {
+    if (which == 1) for (int c = 0; c < 2; c++) for (int k = 0; k < 12; k++) out[c * 12 + k] = G1_GEN[c][k];
+    else for (int c = 0; c < 4; c++) for (int k = 0; k < 12; k++) out[c * 12 + k] = G2_GEN[c][k];
+}
+
+template <class F>
+static int fixed_base_impl(int device, const uint64_t* scalars, size_t n, uint8_t* out) {
+    constexpr bool G2 = (FieldWords<F>::W == 24);
+    const size_t pb = G2 ? MP_G2_BYTES : MP_G1_BYTES;
+    if (n && (!scalars || !out)) return MP_ERR_INVALID_ARG;
+    MP_TRY(use_device(device));
+    if (n == 0) return MP_OK;
+    DevBuf d_s, d_o, d_g;
+    MP_TRY(d_s.alloc(n * 32));
+    MP_TRY(d_o.alloc(n * pb));
+    MP_TRY(d_g.alloc(pb));
+    MP_CUDA_TRY(cudaMemcpy(d_s.p, scalars, n * 32, cudaMemcpyHostToDevice));
+    k_copy_gen<<<1, 1>>>(d_g.as<uint32_t>(), G2 ? 2 : 1);
+    MP_KERNEL_CHECK();
+    k_fixed_base<F><<<div_up(n, 64), 64>>>(d_g.as<uint32_t>(), d_s.as<uint32_t>(), d_o.as<uint32_t>(), n);
+    MP_KERNEL_CHECK();
+    if (G2) MP_TRY(points_to_ark_g2(d_o.p, d_o.p, n, 0));
+    else MP_TRY(points_to_ark_g1(d_o.p, d_o.p, n, 0));
+    MP_CUDA_TRY(cudaMemcpy(out, d_o.p, n * pb, cudaMemcpyDeviceToHost));
+    return MP_OK;
+}
+
+}  // namespace mp
+
+using namespace mp;
+
+extern "C" {
+
+int mp_msm_g1(int device, const uint8_t* bases, const uint64_t* scalars, size_t n, uint8_t out_point[MP_G1_BYTES], float* out_ms) {
+    return msm_standalone<Fq>(device, bases, scalars, n, out_point, out_ms);
+}
+int mp_msm_g2(int device, const uint8_t* bases, const uint64_t* scalars, size_t n, uint8_t out_point[MP_G2_BYTES], float* out_ms) {
+    return msm_standalone<Fq2>(device, bases, scalars, n, out_point, out_ms);
+}
+int mp_fixed_base_g1(int device, const uint64_t* scalars, size_t n, uint8_t* out) { return fixed_base_impl<Fq>(device, scalars, n, out); }
+int mp_fixed_base_g2(int device, const uint64_t* scalars, size_t n, uint8_t* out) { return fixed_base_impl<Fq2>(device, scalars, n, out); }
+
+}  // extern "C"

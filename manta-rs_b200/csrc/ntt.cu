@@ -1,0 +1,402 @@
+// Radix-2 NTT over the BLS12-381 scalar field and the R1CS -> QAP witness map on sm_100a.
+//
+// Replaces ark-poly 0.3 `Radix2EvaluationDomain` in-place transforms and ark-groth16 0.3
+// `R1CStoQAP::witness_map` (reached from manta-crypto/src/arkworks/groth16.rs:597).
+//
+// A transform of n = n1 * n2 points is done in two shared-memory passes (the classic four-step split):
+//   pass 1: for every column i2, an n1-point transform over i1 (stride n2), then the twiddle w_n^(i2*k1);
+//   pass 2: for every row k1, an n2-point transform over i2; the store scatters to natural order k1 + n1*k2.
+// Each pass stages its 2048-element tile and the n/2 twiddles of its sub-transform in shared memory, so the
+// data moves HBM -> SMEM -> HBM exactly twice per transform (once for n <= 1024).  Coset shifts, the 1/n of the
+// inverse, the division by the vanishing polynomial and the final Montgomery -> canonical conversion are all
+// folded into per-element "post" tables applied in the store of pass 2.
+#include <algorithm>
+#include <vector>
+
+#include "ntt.cuh"
+
+namespace mp {
+
+constexpr int NTT_TILE = 2048;      // Fr elements per block tile (64 KiB)
+constexpr int NTT_THREADS = 256;
+constexpr unsigned NTT_MAX_SUB = 10;  // largest in-SMEM sub-transform (2^10 points)
+
+struct NttArgs {
+    const uint32_t* in;
+    uint32_t* out;
+    const uint32_t* tw;     // w^k, k < n
+    const uint32_t* pre;    // nullable, n entries
+    const uint32_t* post;   // nullable, n entries
+    const uint32_t* post_c; // nullable, 1 entry
+    unsigned log_n, l1, l2; // n = 2^log_n = 2^l1 * 2^l2
+    size_t in_stride, out_stride;  // elements between consecutive vectors
+};
+
+MP_DEV unsigned brev_bits(unsigned p, unsigned lg) { return lg ? (__brev(p) >> (32 - lg)) : 0u; }
+
+// In-SMEM decimation-in-frequency transform of `seqs` sequences of 2^lg points.
+// element (j, c) at s[(j * sj + c * sc) * 8]; twiddle w_np^e at tws[e * 8].  Leaves bit-reversed order.
+MP_DEV void smem_dif(uint32_t* s, const uint32_t* tws, unsigned lg, unsigned seqs, unsigned sj, unsigned sc, bool seq_fastest) {
+    const unsigned np = 1u << lg;
+    const unsigned total = (np >> 1) * seqs;
+    for (unsigned st = 0; st < lg; st++) {
+        const unsigned lh = lg - 1 - st, half = 1u << lh;
+        for (unsigned e = threadIdx.x; e < total; e += NTT_THREADS) {
+            unsigned c, bf;
+            if (seq_fastest) { c = e % seqs; bf = e / seqs; }
+            else { bf = e & ((np >> 1) - 1); c = e >> (lg - 1); }
+            unsigned jj = bf & (half - 1), blk = bf >> lh;
+            unsigned i0 = (blk << (lh + 1)) + jj, i1 = i0 + half;
+            uint32_t* p0 = s + (size_t)(i0 * sj + c * sc) * 8;
+            uint32_t* p1 = s + (size_t)(i1 * sj + c * sc) * 8;
+            Fr u = Fr::load(p0), v = Fr::load(p1);
+            (u + v).store(p0);
+            Fr d = u - v;
+            if (jj) d = d * Fr::load(tws + (size_t)(jj << st) * 8);
+            d.store(p1);
+        }
+        __syncthreads();
+    }
+}
+
+// pass 1 (columns): blockIdx.x = column tile, blockIdx.y = vector
+__global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(NttArgs a) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const unsigned n1 = 1u << a.l1, n2 = 1u << a.l2;
+    const unsigned C = min((unsigned)NTT_TILE >> a.l1, n2);
+    const unsigned c0 = blockIdx.x * C;
+    const size_t v = blockIdx.y;
+    uint32_t* tile = smem;
+    uint32_t* tws = smem + (size_t)NTT_TILE * 8;
+    const uint32_t* in = a.in + v * a.in_stride * 8;
+    for (unsigned e = threadIdx.x; e < (n1 >> 1); e += NTT_THREADS) Fr::load(a.tw + ((size_t)e << a.l2) * 8).store(tws + (size_t)e * 8);
+    for (unsigned idx = threadIdx.x; idx < n1 * C; idx += NTT_THREADS) {
+        unsigned c = idx % C, j = idx / C;
+        size_t gi = (size_t)j * n2 + c0 + c;
+        Fr x = Fr::load(in + gi * 8);
+        if (a.pre) x = x * Fr::load(a.pre + gi * 8);
+        x.store(tile + (size_t)idx * 8);
+    }
+    __syncthreads();
+    smem_dif(tile, tws, a.l1, C, C, 1, true);
+    uint32_t* out = a.out + v * a.in_stride * 8;
+    const unsigned nmask = (1u << a.log_n) - 1;
+    for (unsigned idx = threadIdx.x; idx < n1 * C; idx += NTT_THREADS) {
+        unsigned c = idx % C, p = idx / C;
+        unsigned k1 = brev_bits(p, a.l1);
+        Fr x = Fr::load(tile + (size_t)idx * 8);
+        unsigned te = (k1 * (c0 + c)) & nmask;
+        if (te) x = x * Fr::load(a.tw + (size_t)te * 8);
+        x.store(out + ((size_t)k1 * n2 + c0 + c) * 8);
+    }
+}
+
+// pass 2 (rows) — also the whole transform when l1 == 0
+__global__ void __launch_bounds__(NTT_THREADS) k_ntt_rows(NttArgs a) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const unsigned n1 = 1u << a.l1, n2 = 1u << a.l2;
+    const unsigned R = min((unsigned)NTT_TILE >> a.l2, n1);
+    const unsigned r0 = blockIdx.x * R;
+    const size_t v = blockIdx.y;
+    const unsigned rs = n2 + 1;  // padded row stride (elements)
+    uint32_t* tile = smem;
+    uint32_t* tws = smem + (size_t)(NTT_TILE + 64) * 8;
+    const uint32_t* in = a.in + v * a.in_stride * 8;
+    for (unsigned e = threadIdx.x; e < (n2 >> 1); e += NTT_THREADS) Fr::load(a.tw + ((size_t)e << a.l1) * 8).store(tws + (size_t)e * 8);
+    for (unsigned idx = threadIdx.x; idx < n2 * R; idx += NTT_THREADS) {
+        unsigned j = idx & (n2 - 1), c = idx >> a.l2;
+        size_t gi = (size_t)(r0 + c) * n2 + j;
+        Fr x = Fr::load(in + gi * 8);
+        if (a.l1 == 0 && a.pre) x = x * Fr::load(a.pre + gi * 8);
+        x.store(tile + (size_t)(c * rs + j) * 8);
+    }
+    __syncthreads();
+    smem_dif(tile, tws, a.l2, R, 1, rs, false);
+    uint32_t* out = a.out + v * a.out_stride * 8;
+    Fr pc;
+    if (a.post_c) pc = Fr::load(a.post_c);
+    for (unsigned idx = threadIdx.x; idx < n2 * R; idx += NTT_THREADS) {
+        unsigned c = idx % R, p = idx / R;
+        unsigned k2 = brev_bits(p, a.l2);
+        size_t k = (size_t)(r0 + c) + ((size_t)k2 << a.l1);
+        Fr x = Fr::load(tile + (size_t)(c * rs + p) * 8);
+        if (a.post) x = x * Fr::load(a.post + k * 8);
+        else if (a.post_c) x = x * pc;
+        x.store(out + k * 8);
+    }
+}
+
+static size_t ntt_smem_bytes(unsigned lsub) { return ((size_t)NTT_TILE + 64 + (size_t)(1u << lsub) / 2) * 32; }
+
+int ntt_run_strided(const NttDomain& d, bool inverse, const void* in, void* out, void* tmp, size_t count, size_t in_stride,
+                    size_t out_stride, const void* pre, const void* post, const void* post_c, cudaStream_t st) {
+    if (count == 0) return MP_OK;
+    MP_CUDA_TRY(cudaFuncSetAttribute(k_ntt_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_MAX_SUB)));
+    MP_CUDA_TRY(cudaFuncSetAttribute(k_ntt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_MAX_SUB)));
+    NttArgs a{};
+    a.tw = (const uint32_t*)(inverse ? d.tw_inv.p : d.tw_fwd.p);
+    a.pre = (const uint32_t*)pre;
+    a.post = (const uint32_t*)post;
+    a.post_c = (const uint32_t*)post_c;
+    a.log_n = d.log_n;
+    if (d.log_n <= NTT_MAX_SUB) {
+        a.l1 = 0;
+        a.l2 = d.log_n;
+        a.in = (const uint32_t*)in;
+        a.out = (uint32_t*)out;
+        a.in_stride = in_stride;
+        a.out_stride = out_stride;
+        k_ntt_rows<<<dim3(1, (unsigned)count), NTT_THREADS, ntt_smem_bytes(a.l2), st>>>(a);
+        MP_KERNEL_CHECK();
+        return MP_OK;
+    }
+    a.l1 = (d.log_n + 1) / 2;
+    a.l2 = d.log_n - a.l1;
+    if (a.l1 > NTT_MAX_SUB) { set_error_detail("ntt: log_n = %u exceeds %u", d.log_n, 2 * NTT_MAX_SUB); return MP_ERR_UNSUPPORTED; }
+    const unsigned n1 = 1u << a.l1, n2 = 1u << a.l2;
+    const unsigned C = std::min<unsigned>(NTT_TILE >> a.l1, n2), R = std::min<unsigned>(NTT_TILE >> a.l2, n1);
+    NttArgs p1 = a;
+    p1.in = (const uint32_t*)in;
+    p1.out = (uint32_t*)tmp;
+    p1.in_stride = in_stride;   // tmp uses the same stride as in
+    p1.out_stride = in_stride;
+    k_ntt_cols<<<dim3(n2 / C, (unsigned)count), NTT_THREADS, ntt_smem_bytes(a.l1), st>>>(p1);
+    MP_KERNEL_CHECK();
+    NttArgs p2 = a;
+    p2.in = (const uint32_t*)tmp;
+    p2.out = (uint32_t*)out;
+    p2.in_stride = in_stride;
+    p2.out_stride = out_stride;
+    p2.pre = nullptr;
+    k_ntt_rows<<<dim3(n1 / R, (unsigned)count), NTT_THREADS, ntt_smem_bytes(a.l2), st>>>(p2);
+    MP_KERNEL_CHECK();
+    return MP_OK;
+}
+
+int ntt_run(const NttDomain& d, bool inverse, const void* in, void* out, void* tmp, size_t count, const void* pre,
+            const void* post, const void* post_c, cudaStream_t st) {
+    return ntt_run_strided(d, inverse, in, out, tmp, count, d.n, d.n, pre, post, post_c, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// domain tables
+// ---------------------------------------------------------------------------------------------------------
+MP_COLD Fr fr_pow_u64(Fr base, uint64_t e) {
+    Fr r = Fr::one();
+    while (e) {
+        if (e & 1) r = r * base;
+        base = base.sqr();
+        e >>= 1;
+    }
+    return r;
+}
+
+// tw_fwd[k] = w^k, tw_inv[k] = w^-k, and the post tables (see NttDomain)
+__global__ void k_ntt_tables(unsigned log_n, uint32_t* tw_fwd, uint32_t* tw_inv, uint32_t* post_inv, uint32_t* post_a,
+                             uint32_t* post_ci, uint32_t* post_h, uint32_t* pre_coset) {
+    const size_t n = (size_t)1 << log_n;
+    size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    Fr w = Fr::from_const(FR_ROOT_2_32);
+    for (unsigned i = log_n; i < FR_TWO_ADICITY; i++) w = w.sqr();  // w = primitive n-th root
+    Fr g = Fr::from_const(FR_GENERATOR);
+    Fr wk = fr_pow_u64(w, k);
+    wk.store(tw_fwd + k * 8);
+    Fr wi = (k == 0) ? Fr::one() : fr_pow_u64(w, n - k);
+    wi.store(tw_inv + k * 8);
+    // n^-1
+    Fr nn = Fr::zero();
+    nn.l[0] = (uint32_t)n;
+    nn.l[1] = (uint32_t)(n >> 32);
+    Fr ninv = nn.to_mont().inv();
+    if (k == 0) ninv.store(post_inv);
+    Fr gk = fr_pow_u64(g, k);
+    gk.store(pre_coset + k * 8);
+    (gk * ninv).store(post_a + k * 8);
+    Fr gik = gk.inv();
+    Fr ci = gik * ninv;
+    ci.store(post_ci + k * 8);
+    Fr zg = fr_pow_u64(g, n) - Fr::one();  // vanishing polynomial on the coset
+    (ci * zg.inv()).from_mont().store(post_h + k * 8);
+}
+
+int ntt_domain_create(NttDomain& d, unsigned log_n, cudaStream_t st) {
+    if (log_n > 2 * NTT_MAX_SUB) { set_error_detail("ntt: log_n = %u exceeds %u", log_n, 2 * NTT_MAX_SUB); return MP_ERR_UNSUPPORTED; }
+    d.log_n = log_n;
+    d.n = (size_t)1 << log_n;
+    size_t bytes = d.n * 32;
+    MP_TRY(d.tw_fwd.alloc(bytes));
+    MP_TRY(d.tw_inv.alloc(bytes));
+    MP_TRY(d.post_inv.alloc(32));
+    MP_TRY(d.post_coset_a.alloc(bytes));
+    MP_TRY(d.post_coset_inv.alloc(bytes));
+    MP_TRY(d.post_h.alloc(bytes));
+    MP_TRY(d.pre_coset.alloc(bytes));
+    k_ntt_tables<<<div_up(d.n, 64), 64, 0, st>>>(log_n, d.tw_fwd.as<uint32_t>(), d.tw_inv.as<uint32_t>(), d.post_inv.as<uint32_t>(),
+                                               d.post_coset_a.as<uint32_t>(), d.post_coset_inv.as<uint32_t>(),
+                                               d.post_h.as<uint32_t>(), d.pre_coset.as<uint32_t>());
+    MP_KERNEL_CHECK();
+    return MP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Montgomery conversion, R1CS evaluation, pointwise quotient numerator
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_fr_convert(const uint32_t* in, uint32_t* out, size_t n, int to_mont) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr x = Fr::load(in + i * 8);
+    x = to_mont ? x.to_mont() : x.from_mont();
+    x.store(out + i * 8);
+}
+int fr_to_mont(const void* in, void* out, size_t n, cudaStream_t st) {
+    if (!n) return MP_OK;
+    k_fr_convert<<<div_up(n, 256), 256, 0, st>>>((const uint32_t*)in, (uint32_t*)out, n, 1);
+    MP_KERNEL_CHECK();
+    return MP_OK;
+}
+int fr_from_mont(const void* in, void* out, size_t n, cudaStream_t st) {
+    if (!n) return MP_OK;
+    k_fr_convert<<<div_up(n, 256), 256, 0, st>>>((const uint32_t*)in, (uint32_t*)out, n, 0);
+    MP_KERNEL_CHECK();
+    return MP_OK;
+}
+
+struct SpmvArgs {
+    const uint32_t* row_ptr[3];
+    const uint32_t* col[3];
+    const uint32_t* coeff[3];
+};
+
+// blockIdx.y = vector, blockIdx.z = matrix; thread = row of the padded domain
+__global__ void k_r1cs_eval(SpmvArgs a, uint32_t K, uint32_t p, uint32_t m, const uint32_t* __restrict__ z, size_t z_stride, uint32_t* abc) {
+    uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= m) return;
+    const uint32_t v = blockIdx.y, mat = blockIdx.z;
+    const uint32_t* zz = z + (size_t)v * z_stride * 8;
+    Fr acc = Fr::zero();
+    if (row < K) {
+        uint32_t e0 = a.row_ptr[mat][row], e1 = a.row_ptr[mat][row + 1];
+        for (uint32_t e = e0; e < e1; e++) {
+            Fr c = Fr::load(a.coeff[mat] + (size_t)e * 8);
+            Fr x = Fr::load(zz + (size_t)a.col[mat][e] * 8);
+            acc = acc + c * x;
+        }
+    } else if (mat == 0 && row < K + p) {
+        acc = Fr::load(zz + (size_t)(row - K) * 8);
+    }
+    acc.store(abc + (((size_t)v * 3 + mat) * m + row) * 8);
+}
+
+__global__ void k_r1cs_coeff_to_mont(uint32_t* coeff, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) Fr::load(coeff + i * 8).to_mont().store(coeff + i * 8);
+}
+
+int r1cs_upload(R1csDev& r, const mp_r1cs_view* v, cudaStream_t st) {
+    r.p = v->num_instance;
+    r.w = v->num_witness;
+    r.K = v->num_constraints;
+    const uint64_t* rp[3] = {v->a_row_ptr, v->b_row_ptr, v->c_row_ptr};
+    const uint32_t* cl[3] = {v->a_col, v->b_col, v->c_col};
+    const uint64_t* cf[3] = {v->a_coeff, v->b_coeff, v->c_coeff};
+    for (int m = 0; m < 3; m++) {
+        if (!rp[m]) return MP_ERR_INVALID_ARG;
+        size_t nnz = rp[m][r.K];
+        if (nnz >= (1ull << 32)) return MP_ERR_UNSUPPORTED;
+        if (nnz && (!cl[m] || !cf[m])) return MP_ERR_INVALID_ARG;
+        std::vector<uint32_t> rp32(r.K + 1);  // narrow row_ptr to u32
+        for (size_t i = 0; i <= r.K; i++) {
+            if (rp[m][i] > nnz || (i && rp[m][i] < rp[m][i - 1])) return MP_ERR_FORMAT;
+            rp32[i] = (uint32_t)rp[m][i];
+        }
+        for (size_t e = 0; e < nnz; e++)
+            if (cl[m][e] >= r.p + r.w) return MP_ERR_FORMAT;
+        MP_TRY(r.row_ptr[m].alloc((r.K + 1) * 4));
+        MP_TRY(r.col[m].alloc(nnz * 4));
+        MP_TRY(r.coeff[m].alloc(nnz * 32));
+        MP_CUDA_TRY(cudaMemcpyAsync(r.row_ptr[m].p, rp32.data(), (r.K + 1) * 4, cudaMemcpyHostToDevice, st));
+        MP_CUDA_TRY(cudaStreamSynchronize(st));
+        if (nnz) {
+            MP_CUDA_TRY(cudaMemcpyAsync(r.col[m].p, cl[m], nnz * 4, cudaMemcpyHostToDevice, st));
+            MP_CUDA_TRY(cudaMemcpyAsync(r.coeff[m].p, cf[m], nnz * 32, cudaMemcpyHostToDevice, st));
+            k_r1cs_coeff_to_mont<<<div_up(nnz, 256), 256, 0, st>>>(r.coeff[m].as<uint32_t>(), nnz);
+            MP_KERNEL_CHECK();
+        }
+    }
+    MP_CUDA_TRY(cudaStreamSynchronize(st));
+    return MP_OK;
+}
+
+int r1cs_eval(const R1csDev& r, const void* z_mont, size_t z_stride, size_t count, size_t m, void* abc, cudaStream_t st) {
+    if (!count) return MP_OK;
+    SpmvArgs a{};
+    for (int i = 0; i < 3; i++) {
+        a.row_ptr[i] = r.row_ptr[i].as<uint32_t>();
+        a.col[i] = r.col[i].as<uint32_t>();
+        a.coeff[i] = r.coeff[i].as<uint32_t>();
+    }
+    k_r1cs_eval<<<dim3(div_up(m, 128), (unsigned)count, 3), 128, 0, st>>>(a, (uint32_t)r.K, (uint32_t)r.p, (uint32_t)m,
+                                                                       (const uint32_t*)z_mont, z_stride, (uint32_t*)abc);
+    MP_KERNEL_CHECK();
+    return MP_OK;
+}
+
+// s[v][i] = a[v][i] * b[v][i] - c[v][i]
+__global__ void k_quotient_numerator(const uint32_t* __restrict__ abc, uint32_t* out, size_t m, size_t count) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t v = blockIdx.y;
+    if (i >= m) return;
+    const uint32_t* base = abc + v * 3 * m * 8;
+    Fr a = Fr::load(base + i * 8), b = Fr::load(base + (m + i) * 8), c = Fr::load(base + (2 * m + i) * 8);
+    (a * b - c).store(out + (v * m + i) * 8);
+}
+
+int witness_map_run(const NttDomain& d, void* abc, void* s1, void* s2, size_t count, void* out_h, size_t h_stride, cudaStream_t st) {
+    if (!count) return MP_OK;
+    const size_t m = d.n;
+    // a, b, c: ifft then coset shift (g^i / m folded into the store) ...
+    MP_TRY(ntt_run(d, true, abc, s1, s2, count * 3, nullptr, d.post_coset_a.p, nullptr, st));
+    // ... then the forward transform gives the evaluations on the coset
+    MP_TRY(ntt_run(d, false, s1, abc, s2, count * 3, nullptr, nullptr, nullptr, st));
+    k_quotient_numerator<<<dim3(div_up(m, 256), (unsigned)count), 256, 0, st>>>((const uint32_t*)abc, (uint32_t*)s1, m, count);
+    MP_KERNEL_CHECK();
+    // coset_ifft with 1/(m Z(g)) g^-i and the Montgomery -> canonical conversion folded into the store
+    MP_TRY(ntt_run_strided(d, true, s1, out_h, s2, count, m, h_stride, nullptr, d.post_h.p, nullptr, st));
+    return MP_OK;
+}
+
+}  // namespace mp
+
+using namespace mp;
+
+extern "C" int mp_ntt(int device, uint64_t* data, unsigned log_n, int inverse, int coset, float* out_ms) {
+    if (!data) return MP_ERR_INVALID_ARG;
+    MP_TRY(use_device(device));
+    NttDomain d;
+    MP_TRY(ntt_domain_create(d, log_n, 0));
+    size_t bytes = d.n * 32;
+    DevBuf a, b, c;
+    MP_TRY(a.alloc(bytes));
+    MP_TRY(b.alloc(bytes));
+    MP_TRY(c.alloc(bytes));
+    MP_CUDA_TRY(cudaMemcpy(a.p, data, bytes, cudaMemcpyHostToDevice));
+    MP_TRY(fr_to_mont(a.p, a.p, d.n, 0));
+    cudaEvent_t e0, e1;
+    MP_CUDA_TRY(cudaEventCreate(&e0));
+    MP_CUDA_TRY(cudaEventCreate(&e1));
+    MP_CUDA_TRY(cudaEventRecord(e0, 0));
+    const void* pre = (!inverse && coset) ? d.pre_coset.p : nullptr;
+    const void* post = (inverse && coset) ? d.post_coset_inv.p : nullptr;
+    const void* post_c = (inverse && !coset) ? d.post_inv.p : nullptr;
+    MP_TRY(ntt_run(d, inverse != 0, a.p, b.p, c.p, 1, pre, post, post_c, 0));
+    MP_CUDA_TRY(cudaEventRecord(e1, 0));
+    MP_TRY(fr_from_mont(b.p, b.p, d.n, 0));
+    MP_CUDA_TRY(cudaMemcpy(data, b.p, bytes, cudaMemcpyDeviceToHost));
+    float ms = 0;
+    MP_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (out_ms) *out_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return MP_OK;
+}
