@@ -1,0 +1,513 @@
+// Groth16 prover: device-resident proving context, batched proof pipeline and the C ABI around it.
+//
+// Replaces ark-groth16 0.3 `create_proof(circuit, pk, r, s)` as reached from
+// manta-crypto/src/arkworks/groth16.rs:588-600 (`ProofSystem::prove`):
+//
+//   h      = witness_map(A, B, C, z)                                     (ntt.cu)
+//   g_a    = r*delta_1 + a_query[0] + MSM(a_query[1..], z[1..]) + alpha_1
+//   g1_b   = s*delta_1 + b_g1_query[0] + MSM(b_g1_query[1..], z[1..]) + beta_1
+//   g2_b   = s*delta_2 + b_g2_query[0] + MSM(b_g2_query[1..], z[1..]) + beta_2
+//   g_c    = s*g_a + r*g1_b - r*s*delta_1 + MSM(l_query, z[p..]) + MSM(h_query, h)
+//   proof  = compress(g_a) | compress(g2_b) | compress(g_c)               (groth16.rs:184-195)
+//
+// Device formulation: the scalar vector is extended to z' = z | r | s | -rs | 1 and every query table gets four
+// extra columns (delta / alpha / beta, or infinity where a term does not apply), so the fixed terms ride inside
+// the MSMs (z_0 = 1 already selects query[0]).  A, B1, B2 and L then share ONE sorted digit list; H has its own.
+// All tables hold the 16 window multiples 2^(16 t) P, so each MSM is a single 2^15-bucket problem with no Horner
+// step.  Only s*g_a + r*g1_b remains as two 255-bit scalar multiplications in the finishing kernel.
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "msm.cuh"
+#include "ntt.cuh"
+
+namespace mp {
+
+constexpr int PROVE_C = 16;  // window bits of the circuit MSMs
+constexpr int N_EXTRA = 4;   // r, s, -rs, 1
+
+enum Phase { PH_UPLOAD = 0, PH_PREP, PH_WITNESS_MAP, PH_SORT, PH_ACC_G1, PH_ACC_G2, PH_REDUCE, PH_FINISH, PH_COUNT };
+static const char* const kPhaseNames[PH_COUNT] = {"upload",           "prep+r1cs",         "witness_map(ntt)", "msm_sort",
+                                                  "msm_accumulate_g1", "msm_accumulate_g2", "msm_reduce",       "finish"};
+
+}  // namespace mp
+
+using namespace mp;
+
+struct mp_ctx {
+    int device = 0;
+    uint64_t n = 0, p = 0, w = 0, K = 0, m = 0;
+    unsigned log_m = 0;
+    uint32_t zlen = 0;  // n + N_EXTRA
+    R1csDev r1cs;
+    NttDomain dom;
+    MsmGeom gz{}, gh{};
+    DevBuf tab_a, tab_b1, tab_l, tab_h, tab_b2;
+    size_t device_bytes = 0;
+    std::mutex mu;
+};
+
+struct mp_batch {
+    mp_ctx* ctx = nullptr;
+    size_t capacity = 0, count = 0;
+    cudaStream_t st = nullptr;
+    DevBuf z_canon, z_mont, rs, abc, s1, s2, h_canon;
+    DevBuf sort_z_mem, sort_h_mem;
+    MsmSortWs sort_z, sort_h;
+    DevBuf part_a, part_b1, part_l, part_h, part_b2;
+    DevBuf res_g1, res_g2, red_scratch_g1, red_scratch_g2, proofs;
+    cudaEvent_t ev[PH_COUNT + 1] = {};
+    float phase_ms[PH_COUNT] = {};
+    uint64_t launches = 0;
+    bool ran = false;
+};
+
+namespace mp {
+
+// ---------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------
+// z' extras and the Montgomery copy of z used by the R1CS evaluation.  rs: [batch][2][8] canonical.
+__global__ void k_prove_prep(uint32_t* z_canon, uint32_t* z_mont, const uint32_t* __restrict__ rs, uint32_t n, uint32_t zlen) {
+    const uint32_t b = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t* zc = z_canon + (size_t)b * zlen * 8;
+    uint32_t* zm = z_mont + (size_t)b * zlen * 8;
+    if (i < n) {
+        Fr::load(zc + (size_t)i * 8).to_mont().store(zm + (size_t)i * 8);
+    } else if (i == n) {
+        Fr r = Fr::load(rs + (size_t)b * 16), s = Fr::load(rs + (size_t)b * 16 + 8);
+        r.store(zc + (size_t)n * 8);
+        s.store(zc + (size_t)(n + 1) * 8);
+        // -(r s) canonical: mont(r) * s = r*s (canonical), then negate
+        Fr rsv = r.to_mont() * s;
+        rsv.neg().store(zc + (size_t)(n + 2) * 8);
+        Fr one = Fr::zero();
+        one.l[0] = 1;
+        one.store(zc + (size_t)(n + 3) * 8);
+    }
+}
+
+template <class F>
+MP_COLD XYZZ<F> scalar_mul_affine(const Affine<F>& p, const uint32_t* k) {
+    XYZZ<F> r = XYZZ<F>::inf();
+    int bit = 254;
+    while (bit >= 0 && !((k[bit >> 5] >> (bit & 31)) & 1)) bit--;
+    for (; bit >= 0; bit--) {
+        r = r.dbl();
+        if ((k[bit >> 5] >> (bit & 31)) & 1) r = r.add_mixed_cold(p);
+    }
+    return r;
+}
+
+MP_DEV void write_fq_le(uint8_t* out, const Fq& canon) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint32_t v = canon.l[i];
+        out[4 * i] = (uint8_t)v;
+        out[4 * i + 1] = (uint8_t)(v >> 8);
+        out[4 * i + 2] = (uint8_t)(v >> 16);
+        out[4 * i + 3] = (uint8_t)(v >> 24);
+    }
+}
+
+// ark-serialize compressed forms
+MP_COLD void compress_g1(uint8_t* out, const Affine<Fq>& p) {
+    if (p.is_inf()) {
+        for (int i = 0; i < 48; i++) out[i] = 0;
+        out[47] = 0x40;
+        return;
+    }
+    write_fq_le(out, p.x.from_mont());
+    if (Fq::canonical_gt_half(p.y.from_mont())) out[47] |= 0x80;
+}
+MP_COLD void compress_g2(uint8_t* out, const Affine<Fq2>& p) {
+    if (p.is_inf()) {
+        for (int i = 0; i < 96; i++) out[i] = 0;
+        out[95] = 0x40;
+        return;
+    }
+    write_fq_le(out, p.x.c0.from_mont());
+    write_fq_le(out + 48, p.x.c1.from_mont());
+    Fq y1 = p.y.c1.from_mont();
+    bool larger = y1.is_zero() ? Fq::canonical_gt_half(p.y.c0.from_mont()) : Fq::canonical_gt_half(y1);
+    if (larger) out[95] |= 0x80;
+}
+
+// One block per proof, three warps with one active lane each:
+//   warp 0: g_a -> affine, s*g_a        warp 1: g1_b -> affine, r*g1_b        warp 2: g2_b -> affine, L + H
+// then thread 0 assembles g_c and writes the 192 proof bytes.
+// res_g1: [4][batch] XYZZ (A, B1, L, H); res_g2: [batch] XYZZ.
+__global__ void __launch_bounds__(96) k_prove_finish(const XYZZ<Fq>* __restrict__ res_g1, const XYZZ<Fq2>* __restrict__ res_g2,
+                                                    const uint32_t* __restrict__ rs, uint32_t batch, uint8_t* proofs) {
+    __shared__ __align__(16) uint32_t sh_sa[48], sh_rb[48], sh_lh[48];
+    const uint32_t b = blockIdx.x;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* out = proofs + (size_t)b * MP_PROOF_BYTES;
+    const uint32_t* r = rs + (size_t)b * 16;
+    const uint32_t* s = r + 8;
+    if (lane == 0) {
+        if (warp == 0) {
+            Affine<Fq> a = XYZZ<Fq>::load(res_g1 + b).to_affine();
+            compress_g1(out, a);
+            scalar_mul_affine<Fq>(a, s).store(sh_sa);
+        } else if (warp == 1) {
+            Affine<Fq> b1 = XYZZ<Fq>::load(res_g1 + (size_t)batch + b).to_affine();
+            scalar_mul_affine<Fq>(b1, r).store(sh_rb);
+        } else {
+            Affine<Fq2> b2 = XYZZ<Fq2>::load(res_g2 + b).to_affine();
+            compress_g2(out + 48, b2);
+            XYZZ<Fq> lh = XYZZ<Fq>::load(res_g1 + (size_t)2 * batch + b).add(XYZZ<Fq>::load(res_g1 + (size_t)3 * batch + b));
+            lh.store(sh_lh);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        XYZZ<Fq> c = XYZZ<Fq>::load(sh_sa).add(XYZZ<Fq>::load(sh_rb)).add(XYZZ<Fq>::load(sh_lh));
+        compress_g1(out + 144, c.to_affine());
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host helpers
+// ---------------------------------------------------------------------------------------------------------
+// Assemble `stride` affine points on the device: [front_pad x inf | query (len) | inf ... | extras at n..n+3]
+template <bool G2>
+static int assemble_bases(DevBuf& out, size_t stride, size_t front_pad, const uint8_t* query, size_t len, size_t n,
+                          const uint8_t* const extras[N_EXTRA], cudaStream_t st) {
+    const size_t pb = G2 ? MP_G2_BYTES : MP_G1_BYTES;
+    MP_TRY(out.alloc(stride * pb));
+    // ark bytes for infinity: all zero with 0x40 in the last byte -> fill via host staging
+    std::vector<uint8_t> host(stride * pb, 0);
+    for (size_t i = 0; i < stride; i++) host[i * pb + pb - 1] = 0x40;
+    if (len) memcpy(host.data() + front_pad * pb, query, len * pb);
+    for (int e = 0; e < N_EXTRA; e++)
+        if (extras && extras[e]) memcpy(host.data() + (n + e) * pb, extras[e], pb);
+    MP_CUDA_TRY(cudaMemcpyAsync(out.p, host.data(), stride * pb, cudaMemcpyHostToDevice, st));
+    MP_CUDA_TRY(cudaStreamSynchronize(st));
+    if (G2) MP_TRY(points_from_ark_g2(out.p, out.p, stride, st));
+    else MP_TRY(points_from_ark_g1(out.p, out.p, stride, st));
+    return MP_OK;
+}
+
+template <bool G2>
+static int build_table(mp_ctx* c, const MsmGeom& g, DevBuf& table, DevBuf& bases, cudaStream_t st) {
+    const size_t pb = G2 ? MP_G2_BYTES : MP_G1_BYTES;
+    MP_TRY(table.alloc((size_t)g.rows * g.table_stride * pb));
+    c->device_bytes += table.bytes;
+    if (G2) MP_TRY(msm_build_table_g2(g, bases.p, g.table_stride, table.p, st));
+    else MP_TRY(msm_build_table_g1(g, bases.p, g.table_stride, table.p, st));
+    MP_CUDA_TRY(cudaStreamSynchronize(st));
+    bases.release();
+    return MP_OK;
+}
+
+static int ctx_create_impl(const mp_pk_view* pk, const mp_r1cs_view* r1cs, int device, mp_ctx* c) {
+    MP_TRY(use_device(device));
+    c->device = device;
+    c->p = r1cs->num_instance;
+    c->w = r1cs->num_witness;
+    c->K = r1cs->num_constraints;
+    c->n = c->p + c->w;
+    if (c->p == 0 || c->n >= (1u << 26)) { set_error_detail("bad R1CS shape"); return MP_ERR_INVALID_ARG; }
+    if (pk->a_len != c->n || pk->b_g1_len != c->n || pk->b_g2_len != c->n || pk->l_len != c->w) {
+        set_error_detail("proving key does not match the R1CS shape (n=%llu, w=%llu; a=%llu b1=%llu b2=%llu l=%llu)",
+                         (unsigned long long)c->n, (unsigned long long)c->w, (unsigned long long)pk->a_len,
+                         (unsigned long long)pk->b_g1_len, (unsigned long long)pk->b_g2_len, (unsigned long long)pk->l_len);
+        return MP_ERR_INVALID_ARG;
+    }
+    c->log_m = 0;
+    while (((uint64_t)1 << c->log_m) < c->K + c->p) c->log_m++;
+    c->m = (uint64_t)1 << c->log_m;
+    if (pk->h_len + 1 < c->m) { set_error_detail("h_query shorter than m - 1"); return MP_ERR_INVALID_ARG; }
+    c->zlen = (uint32_t)c->n + N_EXTRA;
+    cudaStream_t st = 0;
+    MP_TRY(r1cs_upload(c->r1cs, r1cs, st));
+    MP_TRY(ntt_domain_create(c->dom, c->log_m, st));
+    c->gz = msm_geom(PROVE_C, 1, c->zlen, c->zlen);
+    c->gh = msm_geom(PROVE_C, 1, (uint32_t)c->m, (uint32_t)c->m);
+    {
+        DevBuf bases;
+        const uint8_t* ex_a[N_EXTRA] = {pk->delta_g1, nullptr, nullptr, pk->alpha_g1};
+        MP_TRY(assemble_bases<false>(bases, c->zlen, 0, pk->a_query, c->n, c->n, ex_a, st));
+        MP_TRY(build_table<false>(c, c->gz, c->tab_a, bases, st));
+        const uint8_t* ex_b1[N_EXTRA] = {nullptr, pk->delta_g1, nullptr, pk->beta_g1};
+        MP_TRY(assemble_bases<false>(bases, c->zlen, 0, pk->b_g1_query, c->n, c->n, ex_b1, st));
+        MP_TRY(build_table<false>(c, c->gz, c->tab_b1, bases, st));
+        const uint8_t* ex_l[N_EXTRA] = {nullptr, nullptr, pk->delta_g1, nullptr};
+        MP_TRY(assemble_bases<false>(bases, c->zlen, c->p, pk->l_query, c->w, c->n, ex_l, st));
+        MP_TRY(build_table<false>(c, c->gz, c->tab_l, bases, st));
+        size_t hl = std::min<uint64_t>(pk->h_len, c->m);
+        MP_TRY(assemble_bases<false>(bases, c->m, 0, pk->h_query, hl, c->m, nullptr, st));
+        MP_TRY(build_table<false>(c, c->gh, c->tab_h, bases, st));
+        const uint8_t* ex_b2[N_EXTRA] = {nullptr, pk->delta_g2, nullptr, pk->beta_g2};
+        MP_TRY(assemble_bases<true>(bases, c->zlen, 0, pk->b_g2_query, c->n, c->n, ex_b2, st));
+        MP_TRY(build_table<true>(c, c->gz, c->tab_b2, bases, st));
+    }
+    MP_CUDA_TRY(cudaDeviceSynchronize());
+    return MP_OK;
+}
+
+static int batch_create_impl(mp_ctx* c, size_t cap, mp_batch* b) {
+    MP_TRY(use_device(c->device));
+    b->ctx = c;
+    b->capacity = cap;
+    MP_CUDA_TRY(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
+    for (auto& e : b->ev) MP_CUDA_TRY(cudaEventCreate(&e));
+    const size_t m = c->m;
+    MP_TRY(b->z_canon.alloc(cap * c->zlen * 32));
+    MP_TRY(b->z_mont.alloc(cap * c->zlen * 32));
+    MP_TRY(b->rs.alloc(cap * 64));
+    MP_TRY(b->abc.alloc(cap * 3 * m * 32));
+    MP_TRY(b->s1.alloc(cap * 3 * m * 32));
+    MP_TRY(b->s2.alloc(cap * 3 * m * 32));
+    MP_TRY(b->h_canon.alloc(cap * m * 32));
+    MP_TRY(msm_sort_ws_alloc(b->sort_z, c->gz, cap, b->sort_z_mem));
+    MP_TRY(msm_sort_ws_alloc(b->sort_h, c->gh, cap, b->sort_h_mem));
+    const size_t g1w = XYZZ<Fq>::WORDS * 4, g2w = XYZZ<Fq2>::WORDS * 4;
+    MP_TRY(b->part_a.alloc(cap * c->gz.max_items * g1w));
+    MP_TRY(b->part_b1.alloc(cap * c->gz.max_items * g1w));
+    MP_TRY(b->part_l.alloc(cap * c->gz.max_items * g1w));
+    MP_TRY(b->part_h.alloc(cap * c->gh.max_items * g1w));
+    MP_TRY(b->part_b2.alloc(cap * c->gz.max_items * g2w));
+    MP_TRY(b->res_g1.alloc(4 * cap * g1w));
+    MP_TRY(b->res_g2.alloc(cap * g2w));
+    MP_TRY(b->red_scratch_g1.alloc(std::max(msm_reduce_scratch_bytes(c->gz, cap, 3, false), msm_reduce_scratch_bytes(c->gh, cap, 1, false))));
+    MP_TRY(b->red_scratch_g2.alloc(msm_reduce_scratch_bytes(c->gz, cap, 1, true)));
+    MP_TRY(b->proofs.alloc(cap * MP_PROOF_BYTES));
+    return MP_OK;
+}
+
+static int batch_run_impl(mp_batch* b, float* out_ms) {
+    mp_ctx* c = b->ctx;
+    const size_t cnt = b->count;
+    if (cnt == 0) { if (out_ms) *out_ms = 0; return MP_OK; }
+    MP_TRY(use_device(c->device));
+    cudaStream_t st = b->st;
+    uint64_t launches = 0;
+    const size_t g1w = XYZZ<Fq>::WORDS * 4;
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_PREP], st));
+    k_prove_prep<<<dim3(div_up(c->n + 1, 256), (unsigned)cnt), 256, 0, st>>>(b->z_canon.as<uint32_t>(), b->z_mont.as<uint32_t>(),
+                                                                           b->rs.as<uint32_t>(), (uint32_t)c->n, c->zlen);
+    MP_KERNEL_CHECK();
+    MP_TRY(r1cs_eval(c->r1cs, b->z_mont.p, c->zlen, cnt, c->m, b->abc.p, st));
+    launches += 2;
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_WITNESS_MAP], st));
+    MP_TRY(witness_map_run(c->dom, b->abc.p, b->s1.p, b->s2.p, cnt, b->h_canon.p, c->m, st));
+    launches += (c->log_m > 10 ? 6 : 3) + 1;
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_SORT], st));
+    MP_TRY(msm_sort(c->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_z, st));
+    MP_TRY(msm_sort(c->gh, b->h_canon.as<uint32_t>(), (size_t)c->m * 8, cnt, b->sort_h, st));
+    launches += 6;
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_ACC_G1], st));
+    MsmTables tz{}, th{}, t2{};
+    tz.n_msm = 3;
+    tz.table[0] = c->tab_a.p;  tz.partial[0] = b->part_a.p;  tz.result[0] = b->res_g1.as<char>();
+    tz.table[1] = c->tab_b1.p; tz.partial[1] = b->part_b1.p; tz.result[1] = b->res_g1.as<char>() + cnt * g1w;
+    tz.table[2] = c->tab_l.p;  tz.partial[2] = b->part_l.p;  tz.result[2] = b->res_g1.as<char>() + 2 * cnt * g1w;
+    th.n_msm = 1;
+    th.table[0] = c->tab_h.p;  th.partial[0] = b->part_h.p;  th.result[0] = b->res_g1.as<char>() + 3 * cnt * g1w;
+    t2.n_msm = 1;
+    t2.table[0] = c->tab_b2.p; t2.partial[0] = b->part_b2.p; t2.result[0] = b->res_g2.p;
+    MP_TRY(msm_accumulate_g1(c->gz, b->sort_z, tz, cnt, st));
+    MP_TRY(msm_accumulate_g1(c->gh, b->sort_h, th, cnt, st));
+    launches += 2;
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_ACC_G2], st));
+    MP_TRY(msm_accumulate_g2(c->gz, b->sort_z, t2, cnt, st));
+    launches += 1;
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_REDUCE], st));
+    MP_TRY(msm_reduce_g1(c->gz, b->sort_z, tz, cnt, b->red_scratch_g1.p, st));
+    MP_TRY(msm_reduce_g1(c->gh, b->sort_h, th, cnt, b->red_scratch_g1.p, st));
+    MP_TRY(msm_reduce_g2(c->gz, b->sort_z, t2, cnt, b->red_scratch_g2.p, st));
+    launches += 9;
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_FINISH], st));
+    k_prove_finish<<<(unsigned)cnt, 96, 0, st>>>(b->res_g1.as<XYZZ<Fq>>(), b->res_g2.as<XYZZ<Fq2>>(), b->rs.as<uint32_t>(),
+                                                 (uint32_t)cnt, b->proofs.as<uint8_t>());
+    MP_KERNEL_CHECK();
+    launches += 1;
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_COUNT], st));
+    MP_CUDA_TRY(cudaStreamSynchronize(st));
+    float total = 0;
+    for (int ph = PH_PREP; ph < PH_COUNT; ph++) {
+        MP_CUDA_TRY(cudaEventElapsedTime(&b->phase_ms[ph], b->ev[ph], b->ev[ph + 1]));
+        total += b->phase_ms[ph];
+    }
+    b->launches = launches;
+    b->ran = true;
+    if (out_ms) *out_ms = total;
+    return MP_OK;
+}
+
+}  // namespace mp
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int mp_pk_parse(const uint8_t* data, size_t len, mp_pk_view* out) {
+    if (!data || !out) return MP_ERR_INVALID_ARG;
+    size_t pos = 0;
+    auto take = [&](size_t nbytes, const uint8_t** p) -> bool {
+        if (nbytes > len - pos) return false;
+        *p = data + pos;
+        pos += nbytes;
+        return true;
+    };
+    auto vec = [&](size_t elem, const uint8_t** p, uint64_t* cnt) -> bool {
+        const uint8_t* lp;
+        if (!take(8, &lp)) return false;
+        uint64_t c = 0;
+        memcpy(&c, lp, 8);
+        if (c > (len - pos) / elem) return false;
+        *cnt = c;
+        return take((size_t)c * elem, p);
+    };
+    memset(out, 0, sizeof(*out));
+    bool ok = take(MP_G1_BYTES, &out->alpha_g1) && take(MP_G2_BYTES, &out->beta_g2) && take(MP_G2_BYTES, &out->gamma_g2) &&
+              take(MP_G2_BYTES, &out->delta_g2) && vec(MP_G1_BYTES, &out->gamma_abc_g1, &out->gamma_abc_len) &&
+              take(MP_G1_BYTES, &out->beta_g1) && take(MP_G1_BYTES, &out->delta_g1) && vec(MP_G1_BYTES, &out->a_query, &out->a_len) &&
+              vec(MP_G1_BYTES, &out->b_g1_query, &out->b_g1_len) && vec(MP_G2_BYTES, &out->b_g2_query, &out->b_g2_len) &&
+              vec(MP_G1_BYTES, &out->h_query, &out->h_len) && vec(MP_G1_BYTES, &out->l_query, &out->l_len);
+    if (!ok || pos != len) {
+        mp::set_error_detail("proving key: truncated or trailing bytes (consumed %zu of %zu)", pos, len);
+        return MP_ERR_FORMAT;
+    }
+    return MP_OK;
+}
+
+int mp_ctx_create(const mp_pk_view* pk, const mp_r1cs_view* r1cs, int device, mp_ctx** out) {
+    if (!pk || !r1cs || !out) return MP_ERR_INVALID_ARG;
+    if (!pk->alpha_g1 || !pk->beta_g1 || !pk->beta_g2 || !pk->delta_g1 || !pk->delta_g2 || !pk->a_query || !pk->b_g1_query ||
+        !pk->b_g2_query || !pk->h_query || (!pk->l_query && pk->l_len))
+        return MP_ERR_INVALID_ARG;
+    mp_ctx* c = new (std::nothrow) mp_ctx();
+    if (!c) return MP_ERR_OOM;
+    int rc = ctx_create_impl(pk, r1cs, device, c);
+    if (rc != MP_OK) {
+        delete c;
+        return rc;
+    }
+    c->device_bytes += c->dom.n * 32 * 6;
+    *out = c;
+    return MP_OK;
+}
+
+void mp_ctx_destroy(mp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    delete ctx;
+}
+
+int mp_ctx_info(const mp_ctx* ctx, uint64_t* n_vars, uint64_t* n_instance, uint64_t* domain_size, uint64_t* device_bytes) {
+    if (!ctx) return MP_ERR_INVALID_ARG;
+    if (n_vars) *n_vars = ctx->n;
+    if (n_instance) *n_instance = ctx->p;
+    if (domain_size) *domain_size = ctx->m;
+    if (device_bytes) *device_bytes = ctx->device_bytes;
+    return MP_OK;
+}
+
+int mp_batch_create(mp_ctx* ctx, size_t capacity, mp_batch** out) {
+    if (!ctx || !out || capacity == 0 || capacity > 60000) return MP_ERR_INVALID_ARG;
+    mp_batch* b = new (std::nothrow) mp_batch();
+    if (!b) return MP_ERR_OOM;
+    int rc = batch_create_impl(ctx, capacity, b);
+    if (rc != MP_OK) {
+        mp_batch_destroy(b);
+        return rc;
+    }
+    *out = b;
+    return MP_OK;
+}
+
+void mp_batch_destroy(mp_batch* b) {
+    if (!b) return;
+    if (b->ctx) cudaSetDevice(b->ctx->device);
+    for (auto& e : b->ev)
+        if (e) cudaEventDestroy(e);
+    if (b->st) cudaStreamDestroy(b->st);
+    delete b;
+}
+
+int mp_batch_upload(mp_batch* b, size_t count, const uint64_t* z, const uint64_t* r, const uint64_t* s) {
+    if (!b || count > b->capacity || (count && (!z || !r || !s))) return MP_ERR_INVALID_ARG;
+    mp_ctx* c = b->ctx;
+    MP_TRY(use_device(c->device));
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_UPLOAD], b->st));
+    if (count) {
+        MP_CUDA_TRY(cudaMemcpy2DAsync(b->z_canon.p, (size_t)c->zlen * 32, z, c->n * 32, c->n * 32, count, cudaMemcpyHostToDevice, b->st));
+        MP_CUDA_TRY(cudaMemcpy2DAsync(b->rs.p, 64, r, 32, 32, count, cudaMemcpyHostToDevice, b->st));
+        MP_CUDA_TRY(cudaMemcpy2DAsync(b->rs.as<char>() + 32, 64, s, 32, 32, count, cudaMemcpyHostToDevice, b->st));
+    }
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_PREP], b->st));
+    MP_CUDA_TRY(cudaStreamSynchronize(b->st));
+    MP_CUDA_TRY(cudaEventElapsedTime(&b->phase_ms[PH_UPLOAD], b->ev[PH_UPLOAD], b->ev[PH_PREP]));
+    b->count = count;
+    b->ran = false;
+    return MP_OK;
+}
+
+int mp_batch_run(mp_batch* b, float* out_device_ms) {
+    if (!b) return MP_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(b->ctx->mu);
+    return batch_run_impl(b, out_device_ms);
+}
+
+int mp_batch_download(mp_batch* b, uint8_t* out_proofs) {
+    if (!b || (b->count && !out_proofs)) return MP_ERR_INVALID_ARG;
+    if (!b->ran && b->count) { mp::set_error_detail("mp_batch_download before mp_batch_run"); return MP_ERR_INVALID_ARG; }
+    MP_TRY(use_device(b->ctx->device));
+    if (b->count) MP_CUDA_TRY(cudaMemcpy(out_proofs, b->proofs.p, b->count * MP_PROOF_BYTES, cudaMemcpyDeviceToHost));
+    return MP_OK;
+}
+
+int mp_batch_phase_ms(const mp_batch* b, float* out_ms, int max_phases) {
+    if (!b || !out_ms) return 0;
+    int nph = max_phases < PH_COUNT ? max_phases : PH_COUNT;
+    for (int i = 0; i < nph; i++) out_ms[i] = b->phase_ms[i];
+    return nph;
+}
+
+const char* mp_phase_name(int i) { return (i >= 0 && i < PH_COUNT) ? kPhaseNames[i] : ""; }
+
+uint64_t mp_batch_kernel_launches(const mp_batch* b) { return b ? b->launches : 0; }
+
+int mp_prove_batch(mp_ctx* ctx, size_t count, const uint64_t* z, const uint64_t* r, const uint64_t* s, uint8_t* out_proofs) {
+    if (!ctx) return MP_ERR_INVALID_ARG;
+    if (count == 0) return MP_OK;
+    mp_batch* b = nullptr;
+    MP_TRY(mp_batch_create(ctx, count, &b));
+    int rc = mp_batch_upload(b, count, z, r, s);
+    if (rc == MP_OK) rc = mp_batch_run(b, nullptr);
+    if (rc == MP_OK) rc = mp_batch_download(b, out_proofs);
+    mp_batch_destroy(b);
+    return rc;
+}
+
+int mp_prove(mp_ctx* ctx, const uint64_t* z, const uint64_t r[4], const uint64_t s[4], uint8_t out_proof[MP_PROOF_BYTES]) {
+    return mp_prove_batch(ctx, 1, z, r, s, out_proof);
+}
+
+int mp_witness_map(mp_ctx* ctx, const uint64_t* z, uint64_t* out_h) {
+    if (!ctx || !z || !out_h) return MP_ERR_INVALID_ARG;
+    MP_TRY(use_device(ctx->device));
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const size_t m = ctx->m;
+    DevBuf zc, zm, abc, s1, s2, h;
+    MP_TRY(zc.alloc(ctx->n * 32));
+    MP_TRY(zm.alloc(ctx->n * 32));
+    MP_TRY(abc.alloc(3 * m * 32));
+    MP_TRY(s1.alloc(3 * m * 32));
+    MP_TRY(s2.alloc(3 * m * 32));
+    MP_TRY(h.alloc(m * 32));
+    MP_CUDA_TRY(cudaMemcpy(zc.p, z, ctx->n * 32, cudaMemcpyHostToDevice));
+    MP_TRY(fr_to_mont(zc.p, zm.p, ctx->n, 0));
+    MP_TRY(r1cs_eval(ctx->r1cs, zm.p, ctx->n, 1, m, abc.p, 0));
+    MP_TRY(witness_map_run(ctx->dom, abc.p, s1.p, s2.p, 1, h.p, m, 0));
+    MP_CUDA_TRY(cudaMemcpy(out_h, h.p, m * 32, cudaMemcpyDeviceToHost));
+    return MP_OK;
+}
+
+}  // extern "C"
