@@ -52,23 +52,30 @@ __global__ void k_group_op(int op, const uint32_t* a, const uint32_t* b, const u
 }
 
 // ---- integer-pipe microbenchmarks ----------------------------------------------------------------------
-// 8 independent 64-bit accumulators per thread, each a chain of mad.wide.u32 (IMAD.WIDE.U32).
-__global__ void k_imad_wide(uint64_t* out, uint32_t x, uint32_t y, int iters) {
-    uint64_t acc[8];
+// 4 independent carry chains of 8 fused (mad.lo.cc, madc.hi.cc) pairs per thread: the IMAD.WIDE.U32(.X) shape the
+// Montgomery multiply is made of.  `a` changes every iteration so nothing can be hoisted or strength-reduced.
+__global__ void k_imad_wide(uint32_t* out, uint32_t x, uint32_t y, int iters) {
+    uint32_t acc[4][16];
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] = threadIdx.x + j;
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int j = 0; j < 16; j++) acc[c][j] = threadIdx.x + j + c;
     uint32_t a = x + threadIdx.x, b = y + blockIdx.x;
     for (int it = 0; it < iters; it++) {
+        a = a * 1664525u + 1013904223u;
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int c = 0; c < 4; c++) {
+            mad_wide_cc(acc[c][0], acc[c][1], a, b);
 #pragma unroll
-            for (int j = 0; j < 8; j++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a), "r"(b));
+            for (int j = 2; j < 16; j += 2) madc_wide_cc(acc[c][j], acc[c][j + 1], a, b);
         }
     }
-    uint64_t s = 0;
+    uint32_t s = 0;
 #pragma unroll
-    for (int j = 0; j < 8; j++) s ^= acc[j];
-    if (s == 0x123456789abcdefull) out[0] = s;
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int j = 0; j < 16; j++) s ^= acc[c][j];
+    if (s == 0xdeadbeefu) out[0] = s;
 }
 
 // Production multiply throughput: 4 independent Fq product chains per thread.
@@ -168,23 +175,23 @@ int mp_debug_int_pipe_rate(int device, double* out_wide_mac_per_s, double* out_f
     MP_CUDA_TRY(cudaEventCreate(&e1));
     float ms = 0;
     {
-        const int iters = 2048, threads = 512, blocks = sms * 4;
-        k_imad_wide<<<blocks, threads>>>(sink.as<uint64_t>(), 3, 5, 16);  // warm-up
+        const int iters = 16384, threads = 512, blocks = sms * 2;
+        k_imad_wide<<<blocks, threads>>>(sink.as<uint32_t>(), 3, 5, iters);  // warm-up (also ramps the clocks)
         double best = 0;
         for (int rep = 0; rep < 5; rep++) {
             MP_CUDA_TRY(cudaEventRecord(e0));
-            k_imad_wide<<<blocks, threads>>>(sink.as<uint64_t>(), 3, 5, iters);
+            k_imad_wide<<<blocks, threads>>>(sink.as<uint32_t>(), 3, 5, iters);
             MP_CUDA_TRY(cudaEventRecord(e1));
             MP_CUDA_TRY(cudaEventSynchronize(e1));
             MP_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-            double rate = (double)blocks * threads * iters * 64.0 / (ms * 1e-3);
+            double rate = (double)blocks * threads * iters * 32.0 / (ms * 1e-3);
             if (rate > best) best = rate;
         }
         if (out_wide_mac_per_s) *out_wide_mac_per_s = best;
     }
     {
-        const int iters = 2048, threads = 256, blocks = sms * 8;
-        k_fq_mul_rate<<<blocks, threads>>>(sink.as<uint32_t>(), 8);
+        const int iters = 8192, threads = 256, blocks = sms * 8;
+        k_fq_mul_rate<<<blocks, threads>>>(sink.as<uint32_t>(), iters);
         double best = 0;
         for (int rep = 0; rep < 5; rep++) {
             MP_CUDA_TRY(cudaEventRecord(e0));

@@ -1,0 +1,264 @@
+"""Parity of the CUDA path against the CPU oracle — bit-exact, through the C ABI.  Run with `-m gpu` on the B200."""
+import ctypes
+import json
+import os
+import random
+
+import pytest
+
+from helpers import cref, BLS12_381 as C, oracle_keygen, trapdoor_proof_bytes
+import manta_rs_b200.workload as wl
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _chk(native, rc):
+    native.check(rc)
+
+
+# ---- field and group arithmetic -----------------------------------------------------------------------------
+@pytest.mark.parametrize("field", [0, 1])
+def test_field_ops(native, field):
+    p, limbs = ((C.q, 6), (C.r, 4))[field]
+    rng = random.Random(field)
+    n = 4096
+    a = [rng.randrange(p) for _ in range(n)]
+    b = [rng.randrange(p) for _ in range(n)]
+    a[:4] = [0, p - 1, 1, p - 1]
+    b[:4] = [0, p - 1, p - 1, 1]
+    for op in range(6):
+        out = ctypes.create_string_buffer(n * limbs * 8)
+        _chk(native, native.lib().mp_debug_field_op(0, field, op, native.pack_scalars(a, limbs), native.pack_scalars(b, limbs), out, n))
+        assert native.unpack_scalars(out.raw, limbs) == cref.field_op(field, op, a, b if op < 3 else None), (field, op)
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_group_ops(native, group):
+    from oracle.pyref.curves import Group
+    G = Group(C, group)
+    rng = random.Random(group)
+    n, pb = 48, 96 * group
+    ka = [rng.randrange(1, C.r) for _ in range(n)]
+    kb = [rng.randrange(1, C.r) for _ in range(n)]
+    kb[0], kb[1] = ka[0], C.r - ka[1]            # doubling and inverse cases
+    A = bytearray(cref.fixed_base(group, ka))
+    B = bytearray(cref.fixed_base(group, kb))
+    inf = G.serialize_uncompressed(None)
+    A[2 * pb:3 * pb] = inf
+    B[3 * pb:4 * pb] = inf
+    A[4 * pb:5 * pb] = inf
+    B[4 * pb:5 * pb] = inf
+    ka[2] = ka[4] = 0
+    kb[3] = kb[4] = 0
+    ks = [rng.randrange(C.r) for _ in range(n)]
+    ks[5], ks[6], ks[7] = 0, 1, C.r - 1
+    out = ctypes.create_string_buffer(n * pb)
+    _chk(native, native.lib().mp_debug_group_op(0, group, 0, bytes(A), bytes(B), None, out, n))
+    assert out.raw == cref.fixed_base(group, [(x + y) % C.r for x, y in zip(ka, kb)])
+    _chk(native, native.lib().mp_debug_group_op(0, group, 1, bytes(A), None, None, out, n))
+    assert out.raw == cref.fixed_base(group, [2 * x % C.r for x in ka])
+    _chk(native, native.lib().mp_debug_group_op(0, group, 2, bytes(A), None, native.pack_scalars(ks), out, n))
+    assert out.raw == cref.fixed_base(group, [x * k % C.r for x, k in zip(ka, ks)])
+
+
+def test_fixed_base_matches_oracle(native):
+    rng = random.Random(11)
+    ks = [0, 1, C.r - 1] + [rng.randrange(C.r) for _ in range(200)]
+    for group, fn, pb in ((1, native.lib().mp_fixed_base_g1, 96), (2, native.lib().mp_fixed_base_g2, 192)):
+        out = ctypes.create_string_buffer(len(ks) * pb)
+        _chk(native, fn(0, native.pack_scalars(ks), len(ks), out))
+        assert out.raw == cref.fixed_base(group, ks)
+
+
+# ---- MSM ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("group,n", [(1, 0), (1, 1), (1, 31), (1, 1000), (1, 1 << 14), (2, 0), (2, 1), (2, 600), (2, 1 << 12)])
+def test_msm_vs_oracle(native, group, n):
+    rng = random.Random(100 * group + n)
+    pb = 96 * group
+    ks = [rng.randrange(1, C.r) for _ in range(n)]
+    bases = bytearray(cref.fixed_base(group, ks))
+    sc = [rng.randrange(C.r) for _ in range(n)]
+    if n >= 31:
+        sc[0], sc[1], sc[2], sc[3], sc[4] = 0, 1, C.r - 1, (1 << 128) - 1, 1 << 254
+        from oracle.pyref.curves import Group
+        bases[7 * pb:8 * pb] = Group(C, group).serialize_uncompressed(None)       # infinity base
+        bases[9 * pb:10 * pb] = bases[8 * pb:9 * pb]                               # repeated base, same scalar
+        sc[9] = sc[8]
+        for i in range(10, 20):                                                    # many zeros / ones (ark shortcuts)
+            sc[i] = i & 1
+    out = ctypes.create_string_buffer(pb)
+    ms = ctypes.c_float()
+    fn = native.lib().mp_msm_g1 if group == 1 else native.lib().mp_msm_g2
+    _chk(native, fn(0, bytes(bases), native.pack_scalars(sc), n, out, ctypes.byref(ms)))
+    assert out.raw == cref.msm(group, bytes(bases), sc, threads=8)
+
+
+def test_msm_skewed_scalars(native):
+    """All scalars equal (one giant bucket per window) exercises the segment splitting."""
+    n = 5000
+    rng = random.Random(5)
+    bases = cref.fixed_base(1, [rng.randrange(1, C.r) for _ in range(n)])
+    for val in (1, 3, (1 << 255) % C.r, C.r - 1):
+        sc = [val] * n
+        out = ctypes.create_string_buffer(96)
+        _chk(native, native.lib().mp_msm_g1(0, bases, native.pack_scalars(sc), n, out, None))
+        assert out.raw == cref.msm(1, bases, sc, threads=8)
+
+
+# ---- NTT ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("log_n", [0, 1, 2, 7, 10, 11, 13, 14, 16])
+def test_ntt_vs_oracle(native, log_n):
+    rng = random.Random(log_n)
+    n = 1 << log_n
+    x = [rng.randrange(C.r) for _ in range(n)]
+    x[0] = 0
+    for inverse in (0, 1):
+        for coset in (0, 1):
+            buf = ctypes.create_string_buffer(native.pack_scalars(x), n * 32)
+            _chk(native, native.lib().mp_ntt(0, buf, log_n, inverse, coset, None))
+            assert native.unpack_scalars(buf.raw) == cref.ntt(x, log_n, inverse, coset), (log_n, inverse, coset)
+
+
+def test_ntt_roundtrip_large(native):
+    """Size-independent property at a size the oracle is not run on: ifft(fft(x)) = x, coset too."""
+    log_n = 18
+    n = 1 << log_n
+    rng = random.Random(18)
+    x = [rng.randrange(C.r) for _ in range(n)]
+    packed = native.pack_scalars(x)
+    for coset in (0, 1):
+        buf = ctypes.create_string_buffer(packed, n * 32)
+        _chk(native, native.lib().mp_ntt(0, buf, log_n, 0, coset, None))
+        assert buf.raw != packed
+        _chk(native, native.lib().mp_ntt(0, buf, log_n, 1, coset, None))
+        assert buf.raw == packed
+
+
+# ---- full proofs -------------------------------------------------------------------------------------------------
+def _prove_and_check(native, cs, pk, trap, seeds, rs, ss, oracle_full=True):
+    from manta_rs_b200 import groth16 as g16
+    ctx = g16.ProvingContext.decode(pk)
+    zs = [wl.make_assignment(cs, s) for s in seeds]
+    proofs = g16.Groth16.prove_many_with_randomness(ctx, [g16.R1CS.from_workload(cs, z) for z in zs], rs, ss)
+    op = cref.OracleProver(pk, cs.p, cs.w, cs.a, cs.b, cs.c) if oracle_full else None
+    for z, r, s, pr in zip(zs, rs, ss, proofs):
+        assert pr.to_bytes() == trapdoor_proof_bytes(cs, trap, z, r, s)
+        if op:
+            assert pr.to_bytes() == op.prove(z, r, s, threads=8)
+    single = g16.Groth16.prove_with_randomness(ctx, g16.R1CS.from_workload(cs, zs[0]), rs[0], ss[0])
+    assert single == proofs[0]
+    ctx.close()
+    return proofs
+
+
+@pytest.mark.parametrize("p,w,dist", [(2, 1, "U"), (2, 5, "U"), (3, 60, "R"), (5, 1200, "R"), (7, 3000, "U")])
+def test_prove_small_shapes(native, p, w, dist):
+    cs = wl.make_r1cs(p, w, dist=dist)
+    pk, trap = oracle_keygen(cs, wl.sample_trapdoor(p + w))
+    rng = random.Random(w)
+    rs = [rng.randrange(C.r), 0, C.r - 1]
+    ss = [rng.randrange(C.r), rng.randrange(C.r), 0]
+    _prove_and_check(native, cs, pk, trap, [1, 2, 3], rs, ss)
+
+
+def test_golden_proofs(native):
+    from manta_rs_b200 import groth16 as g16
+    gold = json.load(open(os.path.join(GOLD, "groth16_proofs.json")))
+    for case in gold["cases"]:
+        cs = wl.make_r1cs(case["p"], case["w"], seed=case["seed"], dist=case["dist"])
+        z = wl.make_assignment(cs, case["seed"])
+        pk, _ = oracle_keygen(cs, wl.sample_trapdoor(case["seed"]))
+        ctx = g16.ProvingContext.decode(pk)
+        pr = g16.Groth16.prove_with_randomness(ctx, g16.R1CS.from_workload(cs, z), int(case["r"]), int(case["s"]))
+        assert pr.to_bytes().hex() == case["proof"]
+        ctx.close()
+
+
+def test_prove_with_seeded_chacha_rng_matches_explicit_randomness(native):
+    """`Groth16::prove(context, compiler, rng)` draws r then s from the caller's rng (create_random_proof)."""
+    from manta_rs_b200 import groth16 as g16, rng as mrng
+    cs = wl.make_r1cs(3, 30)
+    pk, trap = oracle_keygen(cs, wl.sample_trapdoor(4))
+    z = wl.make_assignment(cs, 4)
+    ctx = g16.ProvingContext.decode(pk)
+    seed = bytes(range(32))
+    pr = g16.Groth16.prove(ctx, g16.R1CS.from_workload(cs, z), mrng.ChaCha20Rng(seed))
+    r0 = mrng.ChaCha20Rng(seed)
+    r = mrng.field_rand(r0, C.r)
+    s = mrng.field_rand(r0, C.r)
+    assert pr.to_bytes() == trapdoor_proof_bytes(cs, trap, z, r, s)
+    ctx.close()
+
+
+def test_unsatisfied_assignment_matches_oracle(native):
+    from manta_rs_b200 import groth16 as g16
+    cs = wl.make_r1cs(2, 13)
+    pk, _ = oracle_keygen(cs, wl.sample_trapdoor(2))
+    z = wl.make_assignment(cs, 1)
+    z[-1] = (z[-1] + 1) % C.r
+    ctx = g16.ProvingContext.decode(pk)
+    pr = g16.Groth16.prove_with_randomness(ctx, g16.R1CS.from_workload(cs, z), 5, 6)
+    assert pr.to_bytes() == cref.OracleProver(pk, cs.p, cs.w, cs.a, cs.b, cs.c).prove(z, 5, 6)
+    ctx.close()
+
+
+def test_mpc_style_key_with_h_len_m(native):
+    """Production keys come from the MPC and carry m (not m - 1) h_query points (mpc.rs:371-377)."""
+    cs = wl.make_r1cs(3, 29)
+    pk, trap = oracle_keygen(cs, wl.sample_trapdoor(6), h_len=cs.m)
+    _prove_and_check(native, cs, pk, trap, [1], [77], [88])
+
+
+def test_witness_map_vs_oracle(native):
+    from manta_rs_b200 import groth16 as g16
+    cs = wl.make_r1cs(4, 700, dist="R")
+    pk, _ = oracle_keygen(cs, wl.sample_trapdoor(8))
+    z = wl.make_assignment(cs, 8)
+    ctx = g16.ProvingContext.decode(pk)
+    h = ctx.native(g16.R1CS.from_workload(cs, z).matrices)
+    out = ctypes.create_string_buffer(cs.m * 32)
+    _chk(native, native.lib().mp_witness_map(h, native.pack_scalars(z), out))
+    assert native.unpack_scalars(out.raw) == cref.OracleProver(pk, cs.p, cs.w, cs.a, cs.b, cs.c).witness_map(z)
+    ctx.close()
+
+
+@pytest.mark.parametrize("shape,dist", [("to_private", "U"), ("private_transfer", "U"), ("to_public", "R")])
+def test_prove_reference_shapes_full_size(native, shape, dist):
+    """BASELINE.json configs at full size: GPU keygen (checked against the oracle on a sample), batch of 3 proofs,
+    every proof against the trapdoor closed form and the first against the full CPU oracle."""
+    from manta_rs_b200 import groth16 as g16, keygen
+    cs = wl.make_shape(shape, dist=dist)
+    pk, trap = keygen.generate(cs, wl.sample_trapdoor(21))
+    # spot-check the GPU-generated key against the oracle's fixed-base results
+    r = cs.modulus
+    pos_a = 96 + 192 * 3 + 8 + 96 * cs.p + 96 * 2 + 8
+    idx = [0, 1, cs.n // 2, cs.n - 1]
+    assert b"".join(pk[pos_a + 96 * i:pos_a + 96 * (i + 1)] for i in idx) == cref.fixed_base(1, [trap["u"][i] for i in idx])
+    ctx = g16.ProvingContext.decode(pk)
+    zs = [wl.make_assignment(cs, s) for s in (0, 1, 2)]
+    rng = random.Random(3)
+    rs = [rng.randrange(r) for _ in zs]
+    ss = [rng.randrange(r) for _ in zs]
+    proofs = g16.Groth16.prove_many_with_randomness(ctx, [g16.R1CS.from_workload(cs, z) for z in zs], rs, ss)
+    for z, rr, s, pr in zip(zs, rs, ss, proofs):
+        assert pr.to_bytes() == trapdoor_proof_bytes(cs, trap, z, rr, s)
+    op = cref.OracleProver(pk, cs.p, cs.w, cs.a, cs.b, cs.c)
+    assert proofs[0].to_bytes() == op.prove(zs[0], rs[0], ss[0], threads=cref.lib().oracle_max_threads())
+    ctx.close()
+
+
+def test_msm_closed_form_large(native):
+    """2^20-point G1 MSM (BASELINE config 3 regime): bases k_i G from the fixed-base kernel, result must equal
+    (sum k_i s_i) G computed by the oracle."""
+    n = 1 << 20
+    rng = random.Random(20)
+    ks = [rng.randrange(1, C.r) for _ in range(n)]
+    sc = [rng.randrange(C.r) for _ in range(n)]
+    bases = ctypes.create_string_buffer(n * 96)
+    _chk(native, native.lib().mp_fixed_base_g1(0, native.pack_scalars(ks), n, bases))
+    sample = [0, 12345, n - 1]
+    assert b"".join(bases.raw[96 * i:96 * (i + 1)] for i in sample) == cref.fixed_base(1, [ks[i] for i in sample])
+    out = ctypes.create_string_buffer(96)
+    _chk(native, native.lib().mp_msm_g1(0, bases, native.pack_scalars(sc), n, out, None))
+    assert out.raw == cref.fixed_base(1, [sum(k * s for k, s in zip(ks, sc)) % C.r])

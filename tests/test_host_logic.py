@@ -1,0 +1,113 @@
+"""Host-side logic that needs no GPU: rng mirror, workload generator, codecs, the C ABI surface."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from helpers import ROOT, BLS12_381 as C
+import manta_rs_b200.workload as wl
+from manta_rs_b200 import rng as mrng
+
+
+def test_chacha20_known_answer():
+    # djb ChaCha20, all-zero key and nonce, first 64 bytes of key stream (the vector rand_chacha 0.3 reproduces)
+    r = mrng.ChaCha20Rng(bytes(32))
+    assert r.fill_bytes(64).hex() == (
+        "76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7"
+        "da41597c5157488d7724e03fb8d84a376a43b8f41518a11cc387b669b2ee6586")
+    # next_u64 = lo | hi << 32 of consecutive words; straddles buffer refills transparently
+    a, b = mrng.ChaCha20Rng(bytes(range(32))), mrng.ChaCha20Rng(bytes(range(32)))
+    for _ in range(100):
+        lo, hi = b.next_u32(), b.next_u32()
+        assert a.next_u64() == lo | (hi << 32)
+
+
+def test_field_rand_rule():
+    """ark-ff 0.3 `Fr::rand`: limbs from next_u64, shave, reject >= modulus, limbs ARE the Montgomery form."""
+    class Fixed:
+        def __init__(self, vals):
+            self.vals = list(vals)
+
+        def next_u64(self):
+            return self.vals.pop(0)
+
+    R = 1 << 256
+    limbs = [5, 6, 7, (1 << 63) | 9]                       # top bit is shaved off (REPR_SHAVE_BITS = 1)
+    v = 5 | (6 << 64) | (7 << 128) | (9 << 192)
+    assert mrng.field_rand(Fixed(limbs), C.r) == v * pow(R, -1, C.r) % C.r
+    # a draw >= modulus is rejected and redrawn
+    big = [0xFFFFFFFFFFFFFFFF] * 4
+    assert mrng.field_rand(Fixed(big + limbs), C.r) == v * pow(R, -1, C.r) % C.r
+
+
+def test_workload_shapes_and_satisfaction():
+    for name, (n, p, w, log_m) in wl.SHAPES.items():
+        assert n == p + w and (1 << (log_m - 1)) < w + p <= (1 << log_m)
+    cs = wl.make_r1cs(4, 200, dist="R")
+    z = wl.make_assignment(cs, 7)
+    assert z[0] == 1 and wl.is_satisfied(cs, z)
+    assert wl.make_assignment(cs, 7) == z and wl.make_assignment(cs, 8) != z
+    kinds = set(cs.kinds)
+    assert wl.KIND_BOOL in kinds and wl.KIND_MUL in kinds
+    for i, k in enumerate(cs.kinds):
+        if k == wl.KIND_BOOL:
+            assert z[cs.p + i] in (0, 1)
+        if k == wl.KIND_SMALL:
+            assert z[cs.p + i] < (1 << 128)
+    z[-1] = (z[-1] + 1) % C.r
+    assert not wl.is_satisfied(cs, z)
+
+
+def test_header_symbols_exported_and_bound(native):
+    """Every function include/mantaprover.h declares is exported by the built library and bound in _native.py."""
+    hdr = open(os.path.join(ROOT, "include", "mantaprover.h")).read()
+    declared = set(re.findall(r"MP_API [\w\s\*]+?\b(mp_\w+)\(", hdr))
+    assert len(declared) >= 25
+    out = subprocess.run(["nm", "-D", "--defined-only", native.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (mp_\w+)", out))
+    assert declared <= exported, declared - exported
+    assert declared == set(native.SYMBOLS), declared ^ set(native.SYMBOLS)
+    lib = native.lib()
+    assert lib.mp_strerror(0) == b"ok" and b"fallback" in lib.mp_strerror(3)
+
+
+def test_pk_parse_and_errors_without_gpu(native):
+    from oracle.pyref import groth16 as og
+    from manta_rs_b200 import groth16 as g16
+    cs = wl.make_r1cs(2, 6)
+    pk, _ = og.setup_trapdoor(C, cs.as_dict(), *wl.sample_trapdoor(1))
+    pkb = og.pk_to_bytes(C, pk)
+    view = native.PkView()
+    buf = ctypes.create_string_buffer(pkb, len(pkb))
+    assert native.lib().mp_pk_parse(buf, len(pkb), ctypes.byref(view)) == 0
+    assert (view.a_len, view.b_g1_len, view.b_g2_len, view.h_len, view.l_len, view.gamma_abc_len) == (8, 8, 8, 7, 6, 2)
+    base = ctypes.addressof(buf)
+    assert view.alpha_g1 == base and view.beta_g2 == base + 96
+    # truncated / trailing bytes are format errors, never crashes
+    assert native.lib().mp_pk_parse(buf, len(pkb) - 1, ctypes.byref(view)) == 5
+    with pytest.raises(g16.Error):
+        g16.ProvingContext.decode(pkb + b"\0")
+    ctx = g16.ProvingContext.decode(pkb)
+    assert ctx.encode() == pkb and ctx == ctx.clone()
+    # Proof codec: `codec::Encode` wraps the 192 bytes as Vec<u8> (u64-LE length prefix)
+    pr = g16.Proof(bytes(range(192)))
+    assert pr.encode() == (192).to_bytes(8, "little") + bytes(range(192))
+    with pytest.raises(g16.Error):
+        g16.Proof(b"short")
+
+
+def test_no_cpu_fallback_without_device(native):
+    """Without a CUDA device every compute entry point fails loudly (MP_ERR_NO_DEVICE), it never computes on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("device present")
+    out = ctypes.create_string_buffer(96)
+    ms = ctypes.c_float()
+    rc = native.lib().mp_msm_g1(0, None, None, 0, out, ctypes.byref(ms))
+    assert rc in (2, 3)
+    with pytest.raises(native.NativeError):
+        native.check(rc)
+    data = ctypes.create_string_buffer(64)
+    assert native.lib().mp_ntt(0, data, 1, 0, 0, None) in (2, 3)
