@@ -115,6 +115,9 @@ MP_API int mp_batch_download(mp_batch* b, uint8_t* out_proofs);
 MP_API int mp_batch_phase_ms(const mp_batch* b, float* out_ms, int max_phases);
 MP_API const char* mp_phase_name(int i);
 MP_API uint64_t mp_batch_kernel_launches(const mp_batch* b); /* kernels launched by the last mp_batch_run */
+/* overlap = 1 (default): the G2 MSM runs on a second stream next to the G1 MSMs and the witness map; overlap = 0:
+ * every kernel on one stream in program order, so the per-phase CUDA-event times are those of the kernels alone. */
+MP_API int mp_batch_set_overlap(mp_batch* b, int overlap);
 
 /* ---- stand-alone kernels of the path (ark-ec `VariableBaseMSM::multi_scalar_mul`, ark-poly radix-2 domain;
  *      direct reference call sites: manta-benchmark/src/ecc.rs:62-118, manta-trusted-setup/src/groth16/mpc.rs:367-381) */

@@ -56,6 +56,7 @@ struct FqParams {
     MP_DEV static const uint32_t* r2() { return FQ_R2; }
     MP_DEV static const uint32_t* pm2() { return FQ_PM2; }
     MP_DEV static const uint32_t* half() { return FQ_HALF; }
+    MP_DEV static const uint32_t* pshift() { return FQ_PSHIFT; }
 };
 struct FrParams {
     static constexpr int N = 8;
@@ -66,6 +67,7 @@ struct FrParams {
     MP_DEV static const uint32_t* r2() { return FR_R2; }
     MP_DEV static const uint32_t* pm2() { return FR_PM2; }
     MP_DEV static const uint32_t* half() { return FR_HALF; }
+    MP_DEV static const uint32_t* pshift() { return FR_PSHIFT; }
 };
 
 template <class P>
@@ -204,7 +206,7 @@ struct Fp {
         addc(y[N - 1], y[N - 1], 0);
     }
 
-    MP_DEV Fp operator*(const Fp& o) const {
+    MP_DEV Fp mul_cios(const Fp& o) const {
         const uint32_t* m = P::mod();
         // two role-swapping accumulators; after each row the value is divided by 2^32, which turns the
         // odd-position array into the even-position one and shifts the other by two limbs.
@@ -249,6 +251,234 @@ struct Fp {
         r.reduce_once();
         return r;
     }
+
+    // ---- wide (unreduced) products and Montgomery reduction ------------------------------------------
+    // The production multiply is  redc(a (x) b)  with the 2N-limb product built by one level of (subtractive)
+    // Karatsuba over N/2-limb halves: 3 (N/2)^2 + N^2 wide MACs instead of 2 N^2 (N = 12: 252 vs 288).  The
+    // multiplier pipe (IMAD.WIDE: one warp instruction per 4 cycles per sub-partition) is the bottleneck of
+    // every MSM kernel while the ALU pipe idles, so trading MACs for IADD3s is a net win.  Keeping the product
+    // unreduced also lets sums of products share ONE reduction (Fq2, the Y3 coordinate of the point formulas).
+    struct Wide {
+        uint32_t l[2 * N];
+    };
+
+    // schoolbook H x H -> 2H limbs with the even/odd split accumulators (no reduction)
+    template <int H>
+    MP_DEV static void mul_half(uint32_t* t, const uint32_t* a, const uint32_t* b) {
+        uint32_t E[2 * H + 1], O[2 * H];
+#pragma unroll
+        for (int k = 0; k < 2 * H + 1; k++) E[k] = 0;
+#pragma unroll
+        for (int k = 0; k < 2 * H; k++) O[k] = 0;
+        // row 0: plain products
+#pragma unroll
+        for (int j = 0; j < H; j += 2) {
+            mul_wide(E[j], E[j + 1], a[j], b[0]);
+            mul_wide(O[j], O[j + 1], a[j + 1], b[0]);
+        }
+#pragma unroll
+        for (int i = 1; i < H; i++) {
+            const uint32_t bi = b[i];
+            if (i & 1) {
+                // a_even * b_i lands on odd positions: O[i + j - 1], O[i + j]
+                mad_wide_cc(O[i - 1], O[i], a[0], bi);
+#pragma unroll
+                for (int j = 2; j < H; j += 2) madc_wide_cc(O[i + j - 1], O[i + j], a[j], bi);
+                addc(O[i + H - 1], O[i + H - 1], 0);
+                // a_odd * b_i lands on even positions: E[i + j], E[i + j + 1]
+                mad_wide_cc(E[i + 1], E[i + 2], a[1], bi);
+#pragma unroll
+                for (int j = 3; j < H; j += 2) madc_wide_cc(E[i + j], E[i + j + 1], a[j], bi);
+                addc(E[i + H + 1], E[i + H + 1], 0);
+            } else {
+                mad_wide_cc(E[i], E[i + 1], a[0], bi);
+#pragma unroll
+                for (int j = 2; j < H; j += 2) madc_wide_cc(E[i + j], E[i + j + 1], a[j], bi);
+                addc(E[i + H], E[i + H], 0);
+                mad_wide_cc(O[i], O[i + 1], a[1], bi);
+#pragma unroll
+                for (int j = 3; j < H; j += 2) madc_wide_cc(O[i + j - 1], O[i + j], a[j], bi);
+                addc(O[i + H], O[i + H], 0);
+            }
+        }
+        // t = E + (O << 32)
+        t[0] = E[0];
+        add_cc(t[1], E[1], O[0]);
+#pragma unroll
+        for (int k = 2; k < 2 * H - 1; k++) addc_cc(t[k], E[k], O[k - 1]);
+        addc(t[2 * H - 1], E[2 * H - 1], O[2 * H - 2]);
+    }
+
+    // d = x - y over H limbs; returns an all-ones mask when x < y, and then d = y - x (absolute difference)
+    template <int H>
+    MP_DEV static uint32_t abs_diff(uint32_t* d, const uint32_t* x, const uint32_t* y) {
+        sub_cc(d[0], x[0], y[0]);
+#pragma unroll
+        for (int k = 1; k < H; k++) subc_cc(d[k], x[k], y[k]);
+        uint32_t mask;
+        subc(mask, 0, 0);
+        // conditional two's-complement negation: (d ^ mask) + (mask & 1)
+        add_cc(d[0], d[0] ^ mask, mask & 1u);
+#pragma unroll
+        for (int k = 1; k < H - 1; k++) addc_cc(d[k], d[k] ^ mask, 0);
+        addc(d[H - 1], d[H - 1] ^ mask, 0);
+        return mask;
+    }
+
+    // t = a * b (2N limbs); a, b are plain N-limb integers (not necessarily reduced)
+    MP_DEV static void mul_wide_full(uint32_t* t, const uint32_t* a, const uint32_t* b) {
+        constexpr int H = N / 2;
+        uint32_t z0[2 * H], z2[2 * H], zm[2 * H], da[H], db[H];
+        mul_half<H>(z0, a, b);
+        mul_half<H>(z2, a + H, b + H);
+        uint32_t sa = abs_diff<H>(da, a, a + H);      // |a0 - a1|
+        uint32_t sb = abs_diff<H>(db, b + H, b);      // |b1 - b0|
+        mul_half<H>(zm, da, db);
+        const uint32_t neg = sa ^ sb;                 // (a0 - a1)(b1 - b0) is negative
+        // mid = z0 + z2 +- zm = a0 b1 + a1 b0   (2H + 1 limbs)
+        uint32_t mid[2 * H + 1];
+        add_cc(mid[0], z0[0], z2[0]);
+#pragma unroll
+        for (int k = 1; k < 2 * H; k++) addc_cc(mid[k], z0[k], z2[k]);
+        addc(mid[2 * H], 0, 0);
+        add_cc(mid[0], mid[0], neg & 1u);             // + 1 of the two's complement (cannot ripple past mid[2H])
+#pragma unroll
+        for (int k = 1; k < 2 * H; k++) addc_cc(mid[k], mid[k], 0);
+        addc(mid[2 * H], mid[2 * H], 0);
+        add_cc(mid[0], mid[0], zm[0] ^ neg);
+#pragma unroll
+        for (int k = 1; k < 2 * H; k++) addc_cc(mid[k], mid[k], zm[k] ^ neg);
+        addc(mid[2 * H], mid[2 * H], neg);            // sign extension
+        // t = z0 + (mid << 32H) + (z2 << 64H)
+#pragma unroll
+        for (int k = 0; k < H; k++) t[k] = z0[k];
+        add_cc(t[H], z0[H], mid[0]);
+#pragma unroll
+        for (int k = 1; k < H; k++) addc_cc(t[H + k], z0[H + k], mid[k]);
+#pragma unroll
+        for (int k = 0; k < H; k++) addc_cc(t[2 * H + k], z2[k], mid[H + k]);
+        addc_cc(t[3 * H], z2[H], mid[2 * H]);
+#pragma unroll
+        for (int k = 1; k < H - 1; k++) addc_cc(t[3 * H + k], z2[H + k], 0);
+        addc(t[4 * H - 1], z2[2 * H - 1], 0);
+    }
+
+    MP_DEV static Wide mul_wide_w(const Fp& a, const Fp& b) {
+        Wide w;
+#ifdef MP_WIDE_KARATSUBA
+        mul_wide_full(w.l, a.l, b.l);
+#else
+        mul_half<N>(w.l, a.l, b.l);  // schoolbook N x N
+#endif
+        return w;
+    }
+    // w = a + b on 2N limbs (caller guarantees no overflow: sums of a few products of reduced values)
+    MP_DEV static Wide wide_add(const Wide& a, const Wide& b) {
+        Wide w;
+        add_cc(w.l[0], a.l[0], b.l[0]);
+#pragma unroll
+        for (int k = 1; k < 2 * N - 1; k++) addc_cc(w.l[k], a.l[k], b.l[k]);
+        addc(w.l[2 * N - 1], a.l[2 * N - 1], b.l[2 * N - 1]);
+        return w;
+    }
+    // w = a - b on 2N limbs (caller guarantees a >= b)
+    MP_DEV static Wide wide_sub(const Wide& a, const Wide& b) {
+        Wide w;
+        sub_cc(w.l[0], a.l[0], b.l[0]);
+#pragma unroll
+        for (int k = 1; k < 2 * N - 1; k++) subc_cc(w.l[k], a.l[k], b.l[k]);
+        subc(w.l[2 * N - 1], a.l[2 * N - 1], b.l[2 * N - 1]);
+        return w;
+    }
+    // w = a - b + p * 2^bits(p): a multiple of p large enough (>= p^2) to keep a difference of two products of
+    // reduced values non-negative, small enough (< R p / 8) not to disturb the bound of redc.
+    MP_DEV static Wide wide_sub_biased(const Wide& a, const Wide& b) {
+        Wide w;
+        const uint32_t* ps = P::pshift();
+        constexpr int Z = P::BITS / 32;  // low limbs of the bias that are zero
+        sub_cc(w.l[0], a.l[0], b.l[0]);
+#pragma unroll
+        for (int k = 1; k < 2 * N - 1; k++) subc_cc(w.l[k], a.l[k], b.l[k]);
+        subc(w.l[2 * N - 1], a.l[2 * N - 1], b.l[2 * N - 1]);
+        add_cc(w.l[Z], w.l[Z], ps[Z]);
+#pragma unroll
+        for (int k = Z + 1; k < 2 * N - 1; k++) addc_cc(w.l[k], w.l[k], ps[k]);
+        addc(w.l[2 * N - 1], w.l[2 * N - 1], ps[2 * N - 1]);
+        return w;
+    }
+    // a + b without the conditional subtraction (< 2p, still fits N limbs); only as an operand of mul_wide_w
+    MP_DEV static Fp add_noreduce(const Fp& a, const Fp& b) {
+        Fp r;
+        add_cc(r.l[0], a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) addc_cc(r.l[i], a.l[i], b.l[i]);
+        addc(r.l[N - 1], a.l[N - 1], b.l[N - 1]);
+        return r;
+    }
+    // generic "lazy" interface shared with Fq2 (used by the point formulas)
+    MP_DEV static Wide mulw(const Fp& a, const Fp& b) { return mul_wide_w(a, b); }
+    MP_DEV static Wide addw(const Wide& a, const Wide& b) { return wide_add(a, b); }
+    MP_DEV static Fp redcw(const Wide& w) { return redc(w.l); }
+
+    // Montgomery reduction: t / 2^(32 N) mod p for t < 2^(32 N) * p (result fully reduced).
+    // Same split-accumulator rows as mul_cios with the a*b_i rows removed: N^2 wide MACs + N low multiplies.
+    MP_DEV static Fp redc(const uint32_t* t) {
+        const uint32_t* m = P::mod();
+        uint32_t u[N], w[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) u[j] = t[j];
+        // ---- row 0: y array starts at zero, so its products need no carry chain
+        {
+            uint32_t mi = u[0] * P::M0;
+#pragma unroll
+            for (int j = 1; j < N; j += 2) mul_wide(w[j - 1], w[j], m[j], mi);
+            mad_wide_cc(u[0], u[1], m[0], mi);
+#pragma unroll
+            for (int j = 2; j < N; j += 2) madc_wide_cc(u[j], u[j + 1], m[j], mi);
+            addc(w[N - 1], w[N - 1], 0);
+        }
+#pragma unroll
+        for (int i = 1; i < N; i++) {
+            uint32_t* x = (i & 1) ? w : u;   // becomes the even-position array
+            uint32_t* yo = (i & 1) ? u : w;  // old even array: yo[0] == 0, yo[1] folds into x[0], rest shifts by 2
+            add_cc(x[0], x[0], yo[1]);
+            uint32_t mi = x[0] * P::M0;
+#pragma unroll
+            for (int j = 1; j < N - 1; j += 2) madc_wide_cc_from(yo[j - 1], yo[j], m[j], mi, yo[j + 1], yo[j + 2]);
+            madc_wide_top(yo[N - 2], yo[N - 1], m[N - 1], mi);
+            mad_wide_cc(x[0], x[1], m[0], mi);
+#pragma unroll
+            for (int j = 2; j < N; j += 2) madc_wide_cc(x[j], x[j + 1], m[j], mi);
+            addc(yo[N - 1], yo[N - 1], 0);
+        }
+        uint32_t* x = ((N - 1) & 1) ? w : u;
+        uint32_t* y = ((N - 1) & 1) ? u : w;
+        Fp r;
+        add_cc(r.l[0], y[0], x[1]);
+#pragma unroll
+        for (int k = 1; k < N - 1; k++) addc_cc(r.l[k], y[k], x[k + 1]);
+        addc(r.l[N - 1], y[N - 1], 0);
+        // + high half of t
+        add_cc(r.l[0], r.l[0], t[N]);
+#pragma unroll
+        for (int k = 1; k < N - 1; k++) addc_cc(r.l[k], r.l[k], t[N + k]);
+        addc(r.l[N - 1], r.l[N - 1], t[2 * N - 1]);
+        r.reduce_once();
+        return r;
+    }
+    MP_DEV static Fp redc(const Wide& w) { return redc(w.l); }
+
+#ifdef MP_MUL_KARATSUBA
+    MP_DEV Fp operator*(const Fp& o) const {
+        uint32_t t[2 * N];
+        mul_wide_full(t, l, o.l);
+        return redc(t);
+    }
+#else
+    // measured on B200: the interleaved CIOS form wins — IADD3s are not free next to IMAD.WIDE (~1.2 clk each), so
+    // Karatsuba's 36 saved MACs cost more than they save, and its 16 extra registers drop a resident block.
+    MP_DEV Fp operator*(const Fp& o) const { return mul_cios(o); }
+#endif
     MP_DEV Fp sqr() const { return *this * *this; }
 
     // ---- conversions ------------------------------------------------------------------------------

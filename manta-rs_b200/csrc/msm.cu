@@ -4,6 +4,7 @@
 // `create_proof` behind manta-crypto/src/arkworks/groth16.rs:597 and the direct benchmark use at
 // manta-benchmark/src/ecc.rs:62-118.  Only the affine value of the result is observable,
 // so signed digits, precomputed window tables and XYZZ buckets give bit-identical outputs.
+#include <algorithm>
 #include <vector>
 
 #include "msm.cuh"
@@ -13,7 +14,7 @@ namespace mp {
 // ---------------------------------------------------------------------------------------------------------
 // geometry
 // ---------------------------------------------------------------------------------------------------------
-MsmGeom msm_geom(int c, int groups, uint32_t n_scalars, uint32_t table_stride) {
+MsmGeom msm_geom(int c, int groups, uint32_t n_scalars, uint32_t table_stride, size_t batch_hint) {
     MsmGeom g{};
     g.c = c;
     g.windows = 255 / c + 1;
@@ -26,10 +27,14 @@ MsmGeom msm_geom(int c, int groups, uint32_t n_scalars, uint32_t table_stride) {
     g.n_buckets = g.bpg * groups;
     g.max_entries = n_scalars * (uint32_t)g.windows;
     g.max_items = g.n_buckets + g.max_entries / MSM_SEG + 1;
-    uint32_t l1pg = (g.bpg + MSM_RED_S1 - 1) / MSM_RED_S1;
-    uint32_t l2pg = (l1pg + MSM_RED_S2 - 1) / MSM_RED_S2;
-    g.l1_chunks = l1pg * groups;
-    g.l2_chunks = l2pg * groups;
+    // Reduction level 1 is throughput work (2 adds per bucket); its chunk only sets how many threads share it.
+    // Large batches already fill the GPU, so they take long chunks, which shortens the latency-bound level 2.
+    size_t par = (size_t)groups * std::max<size_t>(batch_hint, 1);
+    g.red_s1 = par >= 16 ? 128 : (par >= 4 ? 32 : 8);
+    if (g.red_s1 > g.bpg) g.red_s1 = g.bpg;
+    g.l1pg = (g.bpg + g.red_s1 - 1) / g.red_s1;
+    g.red_d = 1;
+    while (g.red_d * g.red_d < g.l1pg) g.red_d <<= 1;
     return g;
 }
 
@@ -84,10 +89,11 @@ MP_DEV void for_each_digit(const uint32_t* s, int c, int windows, Fn f) {
     }
 }
 
-__global__ void k_msm_hist(MsmGeom g, const uint32_t* __restrict__ scalars, size_t stride_words, uint32_t* cnt) {
+__global__ void k_msm_hist(MsmGeom g, const uint32_t* __restrict__ scalars, size_t stride_words, const uint32_t* __restrict__ valid, uint32_t* cnt) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t b = blockIdx.y;
     if (i >= g.n_scalars) return;
+    if (valid && !((valid[i >> 5] >> (i & 31)) & 1)) return;
     uint32_t s[8];
     const uint4* p = reinterpret_cast<const uint4*>(scalars + b * stride_words + (size_t)i * 8);
     uint4 lo = __ldg(p), hi = __ldg(p + 1);
@@ -99,11 +105,12 @@ __global__ void k_msm_hist(MsmGeom g, const uint32_t* __restrict__ scalars, size
     });
 }
 
-__global__ void k_msm_scatter(MsmGeom g, const uint32_t* __restrict__ scalars, size_t stride_words,
+__global__ void k_msm_scatter(MsmGeom g, const uint32_t* __restrict__ scalars, size_t stride_words, const uint32_t* __restrict__ valid,
                               const uint32_t* __restrict__ start, uint32_t* fill, uint32_t* entries) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t b = blockIdx.y;
     if (i >= g.n_scalars) return;
+    if (valid && !((valid[i >> 5] >> (i & 31)) & 1)) return;
     uint32_t s[8];
     const uint4* p = reinterpret_cast<const uint4*>(scalars + b * stride_words + (size_t)i * 8);
     uint4 lo = __ldg(p), hi = __ldg(p + 1);
@@ -192,16 +199,16 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_msm_plan(MsmGeom g, const uint
 }
 
 int msm_sort(const MsmGeom& g, const uint32_t* scalars, size_t stride_words, size_t batch, const MsmSortWs& ws,
-             cudaStream_t st) {
+             const uint32_t* valid, cudaStream_t st) {
     if (batch == 0 || g.n_scalars == 0) return MP_OK;
     MP_CUDA_TRY(cudaMemsetAsync(ws.cnt, 0, batch * g.n_buckets * 4, st));
     MP_CUDA_TRY(cudaMemsetAsync(ws.fill, 0, batch * g.n_buckets * 4, st));
     dim3 grid(div_up(g.n_scalars, 256), (unsigned)batch);
-    k_msm_hist<<<grid, 256, 0, st>>>(g, scalars, stride_words, ws.cnt);
+    k_msm_hist<<<grid, 256, 0, st>>>(g, scalars, stride_words, valid, ws.cnt);
     MP_KERNEL_CHECK();
     k_msm_plan<<<(unsigned)batch, PLAN_THREADS, 0, st>>>(g, ws.cnt, ws.start, ws.slot_base, (uint2*)ws.items, ws.n_items);
     MP_KERNEL_CHECK();
-    k_msm_scatter<<<grid, 256, 0, st>>>(g, scalars, stride_words, ws.start, ws.fill, ws.entries);
+    k_msm_scatter<<<grid, 256, 0, st>>>(g, scalars, stride_words, valid, ws.start, ws.fill, ws.entries);
     MP_KERNEL_CHECK();
     return MP_OK;
 }
@@ -209,28 +216,50 @@ int msm_sort(const MsmGeom& g, const uint32_t* scalars, size_t stride_words, siz
 // ---------------------------------------------------------------------------------------------------------
 // bucket accumulation: one thread per work item (a bucket, or a <= MSM_SEG slice of a large bucket)
 // ---------------------------------------------------------------------------------------------------------
-struct AccArgs {
-    const void* table[4];
-    void* partial[4];
+struct JobDev {
+    MsmGeom g;
+    const uint32_t *cnt, *start, *slot_base, *n_items, *entries;
+    const uint2* items;
+    const void* table;
+    void* partial;
+    void* result;
+    void* scratch;
 };
+struct JobsArg {
+    JobDev j[MSM_MAX_JOBS];
+};
+static JobsArg make_jobs(const MsmJob* jobs, int n) {
+    JobsArg a{};
+    for (int i = 0; i < n; i++) {
+        a.j[i].g = jobs[i].g;
+        a.j[i].cnt = jobs[i].ws.cnt;
+        a.j[i].start = jobs[i].ws.start;
+        a.j[i].slot_base = jobs[i].ws.slot_base;
+        a.j[i].n_items = jobs[i].ws.n_items;
+        a.j[i].entries = jobs[i].ws.entries;
+        a.j[i].items = (const uint2*)jobs[i].ws.items;
+        a.j[i].table = jobs[i].table;
+        a.j[i].partial = jobs[i].partial;
+        a.j[i].result = jobs[i].result;
+        a.j[i].scratch = jobs[i].scratch;
+    }
+    return a;
+}
 
 template <class F, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_msm_accumulate(MsmGeom g, AccArgs a, const uint32_t* __restrict__ cnt,
-                                                           const uint32_t* __restrict__ start,
-                                                           const uint32_t* __restrict__ slot_base,
-                                                           const uint2* __restrict__ items,
-                                                           const uint32_t* __restrict__ n_items,
-                                                           const uint32_t* __restrict__ entries) {
-    const uint32_t b = blockIdx.y, m = blockIdx.z;
+__global__ void __launch_bounds__(THREADS) k_msm_accumulate(const __grid_constant__ JobsArg jobs) {
+    const JobDev& J = jobs.j[blockIdx.z];
+    const MsmGeom& g = J.g;
+    const uint32_t b = blockIdx.y;
     const uint32_t j = blockIdx.x * THREADS + threadIdx.x;
-    if (j >= n_items[b]) return;
-    const uint2 item = items[(size_t)b * g.max_items + j];
+    if (j >= J.n_items[b]) return;
+    const uint2 item = J.items[(size_t)b * g.max_items + j];
     const uint32_t k = item.x, seg = item.y;
-    const uint32_t total = cnt[(size_t)b * g.n_buckets + k];
+    const uint32_t total = J.cnt[(size_t)b * g.n_buckets + k];
     const uint32_t len = min((uint32_t)MSM_SEG, total - seg * MSM_SEG);
-    const uint32_t* en = entries + (size_t)b * g.max_entries + start[(size_t)b * g.n_buckets + k] + seg * MSM_SEG;
-    const uint32_t slot = slot_base[(size_t)b * (g.n_buckets + 1) + k] + seg;
-    const uint32_t* tab = reinterpret_cast<const uint32_t*>(a.table[m]);
+    const uint32_t* en = J.entries + (size_t)b * g.max_entries + J.start[(size_t)b * g.n_buckets + k] + seg * MSM_SEG;
+    const uint32_t slot = J.slot_base[(size_t)b * (g.n_buckets + 1) + k] + seg;
+    const uint32_t* tab = reinterpret_cast<const uint32_t*>(J.table);
     constexpr int AW = Affine<F>::WORDS;
     XYZZ<F> acc = XYZZ<F>::inf();
     for (uint32_t e = 0; e < len; e++) {
@@ -239,57 +268,54 @@ __global__ void __launch_bounds__(THREADS) k_msm_accumulate(MsmGeom g, AccArgs a
         if (idx >> 31) p.y = p.y.neg();
         acc = acc.add_mixed(p);
     }
-    uint32_t* out = reinterpret_cast<uint32_t*>(a.partial[m]) + ((size_t)b * g.max_items + slot) * XYZZ<F>::WORDS;
+    uint32_t* out = reinterpret_cast<uint32_t*>(J.partial) + ((size_t)b * g.max_items + slot) * XYZZ<F>::WORDS;
     acc.store(out);
 }
 
 template <class F>
-static int accumulate_impl(const MsmGeom& g, const MsmSortWs& ws, const MsmTables& t, size_t batch, cudaStream_t st) {
-    if (batch == 0 || t.n_msm == 0) return MP_OK;
-    AccArgs a{};
-    for (int i = 0; i < t.n_msm; i++) { a.table[i] = t.table[i]; a.partial[i] = t.partial[i]; }
+static int accumulate_impl(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_t st) {
+    if (batch == 0 || n_jobs == 0) return MP_OK;
+    if (n_jobs > MSM_MAX_JOBS) return MP_ERR_INVALID_ARG;
+    JobsArg a = make_jobs(jobs, n_jobs);
     constexpr int THREADS = 128;
-    dim3 grid(div_up(g.max_items, THREADS), (unsigned)batch, (unsigned)t.n_msm);
-    k_msm_accumulate<F, THREADS><<<grid, THREADS, 0, st>>>(g, a, ws.cnt, ws.start, ws.slot_base, (const uint2*)ws.items,
-                                                          ws.n_items, ws.entries);
+    uint32_t max_items = 0;
+    for (int i = 0; i < n_jobs; i++) max_items = std::max(max_items, jobs[i].g.max_items);
+    dim3 grid(div_up(max_items, THREADS), (unsigned)batch, (unsigned)n_jobs);
+    k_msm_accumulate<F, THREADS><<<grid, THREADS, 0, st>>>(a);
     MP_KERNEL_CHECK();
     return MP_OK;
 }
-int msm_accumulate_g1(const MsmGeom& g, const MsmSortWs& ws, const MsmTables& t, size_t batch, cudaStream_t st) {
-    return accumulate_impl<Fq>(g, ws, t, batch, st);
-}
-int msm_accumulate_g2(const MsmGeom& g, const MsmSortWs& ws, const MsmTables& t, size_t batch, cudaStream_t st) {
-    return accumulate_impl<Fq2>(g, ws, t, batch, st);
-}
+int msm_accumulate_g1(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_t st) { return accumulate_impl<Fq>(jobs, n_jobs, batch, st); }
+int msm_accumulate_g2(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_t st) { return accumulate_impl<Fq2>(jobs, n_jobs, batch, st); }
 
 // ---------------------------------------------------------------------------------------------------------
-// bucket reduction  sum_k k * B_k  per window group, three levels of running sums
+// bucket reduction  sum_k k * B_k  per window group
+//   level 1: thread = chunk t of red_s1 buckets -> s_t = sum B, a_t = sum (j+1) B   (running sums; throughput work)
+//   level 2: one block per (job, vector, group): with t = hi * D + lo,
+//              sum_t t s_t = D * sum_hi hi * R_hi + sum_lo lo * C_lo    (R = row sums, C = column sums of s)
+//            total = sum_t a_t + red_s1 * sum_t t s_t
+// scratch per (vector, group): [l1pg][2] level-1 results, then [D][3] (R, C, VA), then [3] partial totals
 // ---------------------------------------------------------------------------------------------------------
-struct RedArgs {
-    const void* partial[4];
-    void* result[4];
-    void* scratch;  // [n_msm][batch][l1_chunks + l2_chunks][3] XYZZ
-};
+MP_DEV size_t red_words_per_group(const MsmGeom& g) { return (size_t)g.l1pg * 2 + (size_t)g.red_d * 3 + 3; }
 
 template <class F>
-MP_DEV XYZZ<F>* red_scratch(const MsmGeom& g, void* scratch, uint32_t m, uint32_t b, uint32_t batch) {
-    size_t per = (size_t)(g.l1_chunks + g.l2_chunks) * 3;
-    return reinterpret_cast<XYZZ<F>*>(scratch) + ((size_t)m * batch + b) * per;
+MP_DEV XYZZ<F>* red_scratch(const JobDev& J, uint32_t b, uint32_t grp) {
+    return reinterpret_cast<XYZZ<F>*>(J.scratch) + ((size_t)b * J.g.groups + grp) * red_words_per_group(J.g);
 }
 
-// level 1: thread = chunk of MSM_RED_S1 buckets -> (s = sum B, a = sum (j+1) B)
 template <class F>
-__global__ void __launch_bounds__(64) k_msm_reduce1(MsmGeom g, RedArgs a, const uint32_t* __restrict__ slot_base, uint32_t batch) {
-    const uint32_t l1pg = g.l1_chunks / g.groups;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // chunk within all groups
-    const uint32_t b = blockIdx.y, m = blockIdx.z;
-    if (t >= g.l1_chunks) return;
-    const uint32_t grp = t / l1pg, tl = t % l1pg;
-    const uint32_t* sb = slot_base + (size_t)b * (g.n_buckets + 1);
-    const XYZZ<F>* part = reinterpret_cast<const XYZZ<F>*>(a.partial[m]) + (size_t)b * g.max_items;
+__global__ void __launch_bounds__(64) k_msm_reduce1(const __grid_constant__ JobsArg jobs) {
+    const JobDev& J = jobs.j[blockIdx.z];
+    const MsmGeom& g = J.g;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // chunk over all groups
+    const uint32_t b = blockIdx.y;
+    if (t >= g.l1pg * g.groups) return;
+    const uint32_t grp = t / g.l1pg, tl = t % g.l1pg;
+    const uint32_t* sb = J.slot_base + (size_t)b * (g.n_buckets + 1);
+    const XYZZ<F>* part = reinterpret_cast<const XYZZ<F>*>(J.partial) + (size_t)b * g.max_items;
     XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
-    for (int j = MSM_RED_S1 - 1; j >= 0; j--) {
-        uint32_t kl = tl * MSM_RED_S1 + j;
+    for (int j = (int)g.red_s1 - 1; j >= 0; j--) {
+        uint32_t kl = tl * g.red_s1 + j;
         if (kl < g.bpg) {
             uint32_t k = grp * g.bpg + kl;
             uint32_t s0 = sb[k], s1 = sb[k + 1];
@@ -297,34 +323,9 @@ __global__ void __launch_bounds__(64) k_msm_reduce1(MsmGeom g, RedArgs a, const 
         }
         acc = acc.add(run);
     }
-    XYZZ<F>* sc = red_scratch<F>(g, a.scratch, m, b, batch);
-    run.store(sc + (size_t)t * 3);
-    acc.store(sc + (size_t)t * 3 + 1);
-}
-
-// level 2: thread = MSM_RED_S2 level-1 chunks -> (rs = sum s, ww = sum (q+1) s, va = sum a)
-template <class F>
-__global__ void __launch_bounds__(32) k_msm_reduce2(MsmGeom g, RedArgs a, uint32_t batch) {
-    const uint32_t l1pg = g.l1_chunks / g.groups, l2pg = g.l2_chunks / g.groups;
-    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t b = blockIdx.y, m = blockIdx.z;
-    if (u >= g.l2_chunks) return;
-    const uint32_t grp = u / l2pg, ul = u % l2pg;
-    XYZZ<F>* sc = red_scratch<F>(g, a.scratch, m, b, batch);
-    XYZZ<F> rs = XYZZ<F>::inf(), ww = XYZZ<F>::inf(), va = XYZZ<F>::inf();
-    for (int q = MSM_RED_S2 - 1; q >= 0; q--) {
-        uint32_t tl = ul * MSM_RED_S2 + q;
-        if (tl < l1pg) {
-            size_t t = (size_t)grp * l1pg + tl;
-            rs = rs.add(XYZZ<F>::load(sc + t * 3));
-            va = va.add(XYZZ<F>::load(sc + t * 3 + 1));
-        }
-        ww = ww.add(rs);
-    }
-    XYZZ<F>* o = sc + (size_t)g.l1_chunks * 3 + (size_t)u * 3;
-    rs.store(o);
-    ww.store(o + 1);
-    va.store(o + 2);
+    XYZZ<F>* sc = red_scratch<F>(J, b, grp);
+    run.store(sc + (size_t)tl * 2);
+    acc.store(sc + (size_t)tl * 2 + 1);
 }
 
 template <class F>
@@ -333,57 +334,109 @@ MP_DEV XYZZ<F> dbl_n(XYZZ<F> p, int n) {
     return p;
 }
 
-// level 3: one thread per (msm, batch, group)
+// blockIdx.x = vector * groups + group, blockIdx.y = job; blockDim.x >= max(red_d, 3)
 template <class F>
-__global__ void __launch_bounds__(32) k_msm_reduce3(MsmGeom g, RedArgs a, uint32_t batch) {
-    const uint32_t l2pg = g.l2_chunks / g.groups;
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;  // over batch * groups
-    const uint32_t m = blockIdx.y;
-    if (idx >= batch * g.groups) return;
-    const uint32_t b = idx / g.groups, grp = idx % g.groups;
-    XYZZ<F>* sc = red_scratch<F>(g, a.scratch, m, b, batch) + (size_t)g.l1_chunks * 3 + (size_t)grp * l2pg * 3;
-    XYZZ<F> R = XYZZ<F>::inf(), Wu = XYZZ<F>::inf(), WW = XYZZ<F>::inf(), VA = XYZZ<F>::inf();
-    for (int u = (int)l2pg - 1; u >= 0; u--) {
-        R = R.add(XYZZ<F>::load(sc + (size_t)u * 3));
-        Wu = Wu.add(R);
-        WW = WW.add(XYZZ<F>::load(sc + (size_t)u * 3 + 1));
-        VA = VA.add(XYZZ<F>::load(sc + (size_t)u * 3 + 2));
+__global__ void __launch_bounds__(64) k_msm_reduce2(const __grid_constant__ JobsArg jobs, uint32_t batch) {
+    const JobDev& J = jobs.j[blockIdx.y];
+    const MsmGeom& g = J.g;
+    if (blockIdx.x >= batch * g.groups) return;
+    const uint32_t b = blockIdx.x / g.groups, grp = blockIdx.x % g.groups;
+    const uint32_t D = g.red_d, tid = threadIdx.x;
+    XYZZ<F>* sc = red_scratch<F>(J, b, grp);
+    XYZZ<F>* rcv = sc + (size_t)g.l1pg * 2;      // [D][3]
+    XYZZ<F>* tot = rcv + (size_t)D * 3;          // [3]
+    if (tid < D) {
+        XYZZ<F> R = XYZZ<F>::inf(), C = XYZZ<F>::inf(), VA = XYZZ<F>::inf();
+        for (uint32_t q = 0; q < D; q++) {
+            uint32_t tr = tid * D + q;   // row tid
+            if (tr < g.l1pg) {
+                R = R.add(XYZZ<F>::load(sc + (size_t)tr * 2));
+                VA = VA.add(XYZZ<F>::load(sc + (size_t)tr * 2 + 1));
+            }
+            uint32_t tc = q * D + tid;   // column tid
+            if (tc < g.l1pg) C = C.add(XYZZ<F>::load(sc + (size_t)tc * 2));
+        }
+        R.store(rcv + (size_t)tid * 3);
+        C.store(rcv + (size_t)tid * 3 + 1);
+        VA.store(rcv + (size_t)tid * 3 + 2);
     }
-    // sum_t t*s_t = S2*Wu + WW - (S2+1)*R ;  total = VA + S1 * that
-    int l2 = 0, l1 = 0;
-    while ((1 << l2) < MSM_RED_S2) l2++;
-    while ((1 << l1) < MSM_RED_S1) l1++;
-    XYZZ<F> T = dbl_n(Wu, l2).add(WW);
-    XYZZ<F> sub = dbl_n(R, l2).add(R);
-    T = T.add(sub.neg());
-    T = dbl_n(T, l1).add(VA);
-    T.store(reinterpret_cast<XYZZ<F>*>(a.result[m]) + (size_t)b * g.groups + grp);
+    __syncthreads();
+    if (tid < 3) {
+        // tid 0: sum_hi hi R_hi, tid 1: sum_lo lo C_lo (running sums from the top), tid 2: sum VA
+        XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
+        if (tid == 2) {
+            for (uint32_t q = 0; q < D; q++) acc = acc.add(XYZZ<F>::load(rcv + (size_t)q * 3 + 2));
+        } else {
+            for (int q = (int)D - 1; q >= 1; q--) {
+                run = run.add(XYZZ<F>::load(rcv + (size_t)q * 3 + tid));
+                acc = acc.add(run);
+            }
+        }
+        acc.store(tot + tid);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int ld = 0, ls = 0;
+        while ((1u << ld) < D) ld++;
+        while ((1u << ls) < g.red_s1) ls++;
+        XYZZ<F> T = dbl_n(XYZZ<F>::load(tot), ld).add(XYZZ<F>::load(tot + 1));
+        // red_s1 is a power of two unless it was clamped to bpg (also a power of two)
+        T = dbl_n(T, ls).add(XYZZ<F>::load(tot + 2));
+        T.store(reinterpret_cast<XYZZ<F>*>(J.result) + (size_t)b * g.groups + grp);
+    }
 }
 
-size_t msm_reduce_scratch_bytes(const MsmGeom& g, size_t batch, int n_msm, bool g2) {
+size_t msm_reduce_scratch_bytes(const MsmGeom& g, size_t batch, bool g2) {
     size_t words = g2 ? XYZZ<Fq2>::WORDS : XYZZ<Fq>::WORDS;
-    return (size_t)n_msm * batch * (g.l1_chunks + g.l2_chunks) * 3 * words * 4;
+    size_t per_group = (size_t)g.l1pg * 2 + (size_t)g.red_d * 3 + 3;
+    return batch * g.groups * per_group * words * 4;
 }
 
 template <class F>
-static int reduce_impl(const MsmGeom& g, const MsmSortWs& ws, const MsmTables& t, size_t batch, void* scratch, cudaStream_t st) {
-    if (batch == 0 || t.n_msm == 0) return MP_OK;
-    RedArgs a{};
-    for (int i = 0; i < t.n_msm; i++) { a.partial[i] = t.partial[i]; a.result[i] = t.result[i]; }
-    a.scratch = scratch;
-    k_msm_reduce1<F><<<dim3(div_up(g.l1_chunks, 64), (unsigned)batch, (unsigned)t.n_msm), 64, 0, st>>>(g, a, ws.slot_base, (uint32_t)batch);
+static int reduce_impl(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_t st) {
+    if (batch == 0 || n_jobs == 0) return MP_OK;
+    if (n_jobs > MSM_MAX_JOBS) return MP_ERR_INVALID_ARG;
+    JobsArg a = make_jobs(jobs, n_jobs);
+    uint32_t max_chunks = 0, max_bg = 0, max_d = 0;
+    for (int i = 0; i < n_jobs; i++) {
+        max_chunks = std::max(max_chunks, jobs[i].g.l1pg * (uint32_t)jobs[i].g.groups);
+        max_bg = std::max(max_bg, (uint32_t)batch * (uint32_t)jobs[i].g.groups);
+        max_d = std::max(max_d, jobs[i].g.red_d);
+    }
+    if (max_d > 64) { set_error_detail("msm reduce: level-2 grid %u exceeds 64", max_d); return MP_ERR_UNSUPPORTED; }
+    k_msm_reduce1<F><<<dim3(div_up(max_chunks, 64), (unsigned)batch, (unsigned)n_jobs), 64, 0, st>>>(a);
     MP_KERNEL_CHECK();
-    k_msm_reduce2<F><<<dim3(div_up(g.l2_chunks, 32), (unsigned)batch, (unsigned)t.n_msm), 32, 0, st>>>(g, a, (uint32_t)batch);
-    MP_KERNEL_CHECK();
-    k_msm_reduce3<F><<<dim3(div_up(batch * g.groups, 32), (unsigned)t.n_msm), 32, 0, st>>>(g, a, (uint32_t)batch);
+    unsigned th = std::max(32u, max_d);
+    k_msm_reduce2<F><<<dim3(max_bg, (unsigned)n_jobs), th, 0, st>>>(a, (uint32_t)batch);
     MP_KERNEL_CHECK();
     return MP_OK;
 }
-int msm_reduce_g1(const MsmGeom& g, const MsmSortWs& ws, const MsmTables& t, size_t batch, void* scratch, cudaStream_t st) {
-    return reduce_impl<Fq>(g, ws, t, batch, scratch, st);
+int msm_reduce_g1(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_t st) { return reduce_impl<Fq>(jobs, n_jobs, batch, st); }
+int msm_reduce_g2(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_t st) { return reduce_impl<Fq2>(jobs, n_jobs, batch, st); }
+
+// ---------------------------------------------------------------------------------------------------------
+// validity bitmaps
+// ---------------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void k_msm_validity(const uint32_t* __restrict__ bases, uint32_t n, uint32_t* bitmap, int accumulate) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool v = false;
+    if (i < n) v = !Affine<F>::load(bases + (size_t)i * Affine<F>::WORDS).is_inf();
+    uint32_t word = __ballot_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && (i >> 5) < (n + 31) / 32) {
+        if (accumulate) bitmap[i >> 5] |= word;
+        else bitmap[i >> 5] = word;
+    }
 }
-int msm_reduce_g2(const MsmGeom& g, const MsmSortWs& ws, const MsmTables& t, size_t batch, void* scratch, cudaStream_t st) {
-    return reduce_impl<Fq2>(g, ws, t, batch, scratch, st);
+int msm_validity_g1(const void* bases, uint32_t n, uint32_t* bitmap, bool accumulate, cudaStream_t st) {
+    k_msm_validity<Fq><<<div_up(n, 256), 256, 0, st>>>((const uint32_t*)bases, n, bitmap, accumulate ? 1 : 0);
+    MP_KERNEL_CHECK();
+    return MP_OK;
+}
+int msm_validity_g2(const void* bases, uint32_t n, uint32_t* bitmap, bool accumulate, cudaStream_t st) {
+    k_msm_validity<Fq2><<<div_up(n, 256), 256, 0, st>>>((const uint32_t*)bases, n, bitmap, accumulate ? 1 : 0);
+    MP_KERNEL_CHECK();
+    return MP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -469,7 +522,7 @@ static int msm_standalone(int device, const uint8_t* bases, const uint64_t* scal
         if (out_ms) *out_ms = 0;
         return MP_OK;
     }
-    MsmGeom g = msm_geom(pick_window(n), 0, (uint32_t)n, (uint32_t)n);
+    MsmGeom g = msm_geom(pick_window(n), 0, (uint32_t)n, (uint32_t)n, 1);
     DevBuf d_bases, d_scalars, d_sort, d_partial, d_result, d_scratch, d_out;
     MP_TRY(d_bases.alloc(n * pb));
     MP_TRY(d_scalars.alloc(n * 32));
@@ -477,7 +530,7 @@ static int msm_standalone(int device, const uint8_t* bases, const uint64_t* scal
     MP_TRY(msm_sort_ws_alloc(ws, g, 1, d_sort));
     MP_TRY(d_partial.alloc((size_t)g.max_items * XYZZ<F>::WORDS * 4));
     MP_TRY(d_result.alloc((size_t)g.groups * XYZZ<F>::WORDS * 4));
-    MP_TRY(d_scratch.alloc(msm_reduce_scratch_bytes(g, 1, 1, G2)));
+    MP_TRY(d_scratch.alloc(msm_reduce_scratch_bytes(g, 1, G2)));
     MP_TRY(d_out.alloc(XYZZ<F>::WORDS * 4 + pb));
     MP_CUDA_TRY(cudaMemcpy(d_bases.p, bases, n * pb, cudaMemcpyHostToDevice));
     MP_CUDA_TRY(cudaMemcpy(d_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice));
@@ -487,19 +540,21 @@ static int msm_standalone(int device, const uint8_t* bases, const uint64_t* scal
     MP_CUDA_TRY(cudaEventCreate(&e0));
     MP_CUDA_TRY(cudaEventCreate(&e1));
     MP_CUDA_TRY(cudaEventRecord(e0, 0));
-    MP_TRY(msm_sort(g, d_scalars.as<uint32_t>(), n * 8, 1, ws, 0));
-    MsmTables t{};
-    t.n_msm = 1;
-    t.table[0] = d_bases.p;
-    t.partial[0] = d_partial.p;
-    t.result[0] = d_result.p;
+    MP_TRY(msm_sort(g, d_scalars.as<uint32_t>(), n * 8, 1, ws, nullptr, 0));
+    MsmJob t{};
+    t.g = g;
+    t.ws = ws;
+    t.table = d_bases.p;
+    t.partial = d_partial.p;
+    t.result = d_result.p;
+    t.scratch = d_scratch.p;
     if (G2) {
-        MP_TRY(msm_accumulate_g2(g, ws, t, 1, 0));
-        MP_TRY(msm_reduce_g2(g, ws, t, 1, d_scratch.p, 0));
+        MP_TRY(msm_accumulate_g2(&t, 1, 1, 0));
+        MP_TRY(msm_reduce_g2(&t, 1, 1, 0));
         MP_TRY(msm_horner_g2(g, d_result.p, d_out.p, 1, 0));
     } else {
-        MP_TRY(msm_accumulate_g1(g, ws, t, 1, 0));
-        MP_TRY(msm_reduce_g1(g, ws, t, 1, d_scratch.p, 0));
+        MP_TRY(msm_accumulate_g1(&t, 1, 1, 0));
+        MP_TRY(msm_reduce_g1(&t, 1, 1, 0));
         MP_TRY(msm_horner_g1(g, d_result.p, d_out.p, 1, 0));
     }
     MP_CUDA_TRY(cudaEventRecord(e1, 0));

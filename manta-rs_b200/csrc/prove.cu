@@ -44,6 +44,7 @@ struct mp_ctx {
     NttDomain dom;
     MsmGeom gz{}, gh{};
     DevBuf tab_a, tab_b1, tab_l, tab_h, tab_b2;
+    DevBuf valid_a, valid_b, valid_l, valid_h;  // per-table "base is not infinity" bitmaps
     size_t device_bytes = 0;
     std::mutex mu;
 };
@@ -51,12 +52,15 @@ struct mp_ctx {
 struct mp_batch {
     mp_ctx* ctx = nullptr;
     size_t capacity = 0, count = 0;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st2 = nullptr;  // main stream; second stream for the G2 path
+    cudaEvent_t ev_z = nullptr, ev_sort_b = nullptr, ev_g2 = nullptr, ev_g2_acc0 = nullptr, ev_g2_acc1 = nullptr;
+    bool overlap = true;
     DevBuf z_canon, z_mont, rs, abc, s1, s2, h_canon;
-    DevBuf sort_z_mem, sort_h_mem;
-    MsmSortWs sort_z, sort_h;
+    DevBuf sort_a_mem, sort_b_mem, sort_l_mem, sort_h_mem;
+    MsmSortWs sort_a, sort_b, sort_l, sort_h;  // A | B1+B2 | L | H each get a list without their infinity bases
     DevBuf part_a, part_b1, part_l, part_h, part_b2;
-    DevBuf res_g1, res_g2, red_scratch_g1, red_scratch_g2, proofs;
+    DevBuf res_g1, res_g2, red_a, red_b1, red_l, red_h, red_b2, proofs;
+    MsmGeom gz{}, gh{};
     cudaEvent_t ev[PH_COUNT + 1] = {};
     float phase_ms[PH_COUNT] = {};
     uint64_t launches = 0;
@@ -192,10 +196,13 @@ static int assemble_bases(DevBuf& out, size_t stride, size_t front_pad, const ui
 }
 
 template <bool G2>
-static int build_table(mp_ctx* c, const MsmGeom& g, DevBuf& table, DevBuf& bases, cudaStream_t st) {
+static int build_table(mp_ctx* c, const MsmGeom& g, DevBuf& table, DevBuf& bases, DevBuf& valid, bool valid_accumulate, cudaStream_t st) {
     const size_t pb = G2 ? MP_G2_BYTES : MP_G1_BYTES;
     MP_TRY(table.alloc((size_t)g.rows * g.table_stride * pb));
     c->device_bytes += table.bytes;
+    if (!valid_accumulate) MP_TRY(valid.alloc(((size_t)g.table_stride + 31) / 32 * 4));
+    if (G2) MP_TRY(msm_validity_g2(bases.p, g.table_stride, valid.as<uint32_t>(), valid_accumulate, st));
+    else MP_TRY(msm_validity_g1(bases.p, g.table_stride, valid.as<uint32_t>(), valid_accumulate, st));
     if (G2) MP_TRY(msm_build_table_g2(g, bases.p, g.table_stride, table.p, st));
     else MP_TRY(msm_build_table_g1(g, bases.p, g.table_stride, table.p, st));
     MP_CUDA_TRY(cudaStreamSynchronize(st));
@@ -225,25 +232,25 @@ static int ctx_create_impl(const mp_pk_view* pk, const mp_r1cs_view* r1cs, int d
     cudaStream_t st = 0;
     MP_TRY(r1cs_upload(c->r1cs, r1cs, st));
     MP_TRY(ntt_domain_create(c->dom, c->log_m, st));
-    c->gz = msm_geom(PROVE_C, 1, c->zlen, c->zlen);
-    c->gh = msm_geom(PROVE_C, 1, (uint32_t)c->m, (uint32_t)c->m);
+    c->gz = msm_geom(PROVE_C, 1, c->zlen, c->zlen, 1);
+    c->gh = msm_geom(PROVE_C, 1, (uint32_t)c->m, (uint32_t)c->m, 1);
     {
         DevBuf bases;
         const uint8_t* ex_a[N_EXTRA] = {pk->delta_g1, nullptr, nullptr, pk->alpha_g1};
         MP_TRY(assemble_bases<false>(bases, c->zlen, 0, pk->a_query, c->n, c->n, ex_a, st));
-        MP_TRY(build_table<false>(c, c->gz, c->tab_a, bases, st));
+        MP_TRY(build_table<false>(c, c->gz, c->tab_a, bases, c->valid_a, false, st));
         const uint8_t* ex_b1[N_EXTRA] = {nullptr, pk->delta_g1, nullptr, pk->beta_g1};
         MP_TRY(assemble_bases<false>(bases, c->zlen, 0, pk->b_g1_query, c->n, c->n, ex_b1, st));
-        MP_TRY(build_table<false>(c, c->gz, c->tab_b1, bases, st));
+        MP_TRY(build_table<false>(c, c->gz, c->tab_b1, bases, c->valid_b, false, st));
         const uint8_t* ex_l[N_EXTRA] = {nullptr, nullptr, pk->delta_g1, nullptr};
         MP_TRY(assemble_bases<false>(bases, c->zlen, c->p, pk->l_query, c->w, c->n, ex_l, st));
-        MP_TRY(build_table<false>(c, c->gz, c->tab_l, bases, st));
+        MP_TRY(build_table<false>(c, c->gz, c->tab_l, bases, c->valid_l, false, st));
         size_t hl = std::min<uint64_t>(pk->h_len, c->m);
         MP_TRY(assemble_bases<false>(bases, c->m, 0, pk->h_query, hl, c->m, nullptr, st));
-        MP_TRY(build_table<false>(c, c->gh, c->tab_h, bases, st));
+        MP_TRY(build_table<false>(c, c->gh, c->tab_h, bases, c->valid_h, false, st));
         const uint8_t* ex_b2[N_EXTRA] = {nullptr, pk->delta_g2, nullptr, pk->beta_g2};
         MP_TRY(assemble_bases<true>(bases, c->zlen, 0, pk->b_g2_query, c->n, c->n, ex_b2, st));
-        MP_TRY(build_table<true>(c, c->gz, c->tab_b2, bases, st));
+        MP_TRY(build_table<true>(c, c->gz, c->tab_b2, bases, c->valid_b, true, st));  // B list keeps a scalar if either B1 or B2 base is finite
     }
     MP_CUDA_TRY(cudaDeviceSynchronize());
     return MP_OK;
@@ -254,7 +261,9 @@ static int batch_create_impl(mp_ctx* c, size_t cap, mp_batch* b) {
     b->ctx = c;
     b->capacity = cap;
     MP_CUDA_TRY(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
+    MP_CUDA_TRY(cudaStreamCreateWithFlags(&b->st2, cudaStreamNonBlocking));
     for (auto& e : b->ev) MP_CUDA_TRY(cudaEventCreate(&e));
+    for (cudaEvent_t* e : {&b->ev_z, &b->ev_sort_b, &b->ev_g2, &b->ev_g2_acc0, &b->ev_g2_acc1}) MP_CUDA_TRY(cudaEventCreate(e));
     const size_t m = c->m;
     MP_TRY(b->z_canon.alloc(cap * c->zlen * 32));
     MP_TRY(b->z_mont.alloc(cap * c->zlen * 32));
@@ -263,18 +272,25 @@ static int batch_create_impl(mp_ctx* c, size_t cap, mp_batch* b) {
     MP_TRY(b->s1.alloc(cap * 3 * m * 32));
     MP_TRY(b->s2.alloc(cap * 3 * m * 32));
     MP_TRY(b->h_canon.alloc(cap * m * 32));
-    MP_TRY(msm_sort_ws_alloc(b->sort_z, c->gz, cap, b->sort_z_mem));
-    MP_TRY(msm_sort_ws_alloc(b->sort_h, c->gh, cap, b->sort_h_mem));
+    b->gz = msm_geom(PROVE_C, 1, c->zlen, c->zlen, cap);
+    b->gh = msm_geom(PROVE_C, 1, (uint32_t)c->m, (uint32_t)c->m, cap);
+    MP_TRY(msm_sort_ws_alloc(b->sort_a, b->gz, cap, b->sort_a_mem));
+    MP_TRY(msm_sort_ws_alloc(b->sort_b, b->gz, cap, b->sort_b_mem));
+    MP_TRY(msm_sort_ws_alloc(b->sort_l, b->gz, cap, b->sort_l_mem));
+    MP_TRY(msm_sort_ws_alloc(b->sort_h, b->gh, cap, b->sort_h_mem));
     const size_t g1w = XYZZ<Fq>::WORDS * 4, g2w = XYZZ<Fq2>::WORDS * 4;
-    MP_TRY(b->part_a.alloc(cap * c->gz.max_items * g1w));
-    MP_TRY(b->part_b1.alloc(cap * c->gz.max_items * g1w));
-    MP_TRY(b->part_l.alloc(cap * c->gz.max_items * g1w));
-    MP_TRY(b->part_h.alloc(cap * c->gh.max_items * g1w));
-    MP_TRY(b->part_b2.alloc(cap * c->gz.max_items * g2w));
+    MP_TRY(b->part_a.alloc(cap * b->gz.max_items * g1w));
+    MP_TRY(b->part_b1.alloc(cap * b->gz.max_items * g1w));
+    MP_TRY(b->part_l.alloc(cap * b->gz.max_items * g1w));
+    MP_TRY(b->part_h.alloc(cap * b->gh.max_items * g1w));
+    MP_TRY(b->part_b2.alloc(cap * b->gz.max_items * g2w));
     MP_TRY(b->res_g1.alloc(4 * cap * g1w));
     MP_TRY(b->res_g2.alloc(cap * g2w));
-    MP_TRY(b->red_scratch_g1.alloc(std::max(msm_reduce_scratch_bytes(c->gz, cap, 3, false), msm_reduce_scratch_bytes(c->gh, cap, 1, false))));
-    MP_TRY(b->red_scratch_g2.alloc(msm_reduce_scratch_bytes(c->gz, cap, 1, true)));
+    MP_TRY(b->red_a.alloc(msm_reduce_scratch_bytes(b->gz, cap, false)));
+    MP_TRY(b->red_b1.alloc(msm_reduce_scratch_bytes(b->gz, cap, false)));
+    MP_TRY(b->red_l.alloc(msm_reduce_scratch_bytes(b->gz, cap, false)));
+    MP_TRY(b->red_h.alloc(msm_reduce_scratch_bytes(b->gh, cap, false)));
+    MP_TRY(b->red_b2.alloc(msm_reduce_scratch_bytes(b->gz, cap, true)));
     MP_TRY(b->proofs.alloc(cap * MP_PROOF_BYTES));
     return MP_OK;
 }
@@ -287,40 +303,65 @@ static int batch_run_impl(mp_batch* b, float* out_ms) {
     cudaStream_t st = b->st;
     uint64_t launches = 0;
     const size_t g1w = XYZZ<Fq>::WORDS * 4;
+    cudaStream_t sg2 = b->overlap ? b->st2 : st;  // stream of the G2 path
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_PREP], st));
     k_prove_prep<<<dim3(div_up(c->n + 1, 256), (unsigned)cnt), 256, 0, st>>>(b->z_canon.as<uint32_t>(), b->z_mont.as<uint32_t>(),
                                                                            b->rs.as<uint32_t>(), (uint32_t)c->n, c->zlen);
     MP_KERNEL_CHECK();
+    MP_CUDA_TRY(cudaEventRecord(b->ev_z, st));  // z' complete: the z-lists can be sorted
+    char* res1 = b->res_g1.as<char>();
+    MsmJob g1[4] = {
+        {b->gz, b->sort_a, c->tab_a.p, b->part_a.p, res1, b->red_a.p},
+        {b->gz, b->sort_b, c->tab_b1.p, b->part_b1.p, res1 + cnt * g1w, b->red_b1.p},
+        {b->gz, b->sort_l, c->tab_l.p, b->part_l.p, res1 + 2 * cnt * g1w, b->red_l.p},
+        {b->gh, b->sort_h, c->tab_h.p, b->part_h.p, res1 + 3 * cnt * g1w, b->red_h.p},
+    };
+    MsmJob g2[1] = {{b->gz, b->sort_b, c->tab_b2.p, b->part_b2.p, b->res_g2.p, b->red_b2.p}};
+    auto g2_path = [&]() -> int {
+        // B list -> G2 accumulate -> G2 reduce (independent of the witness map)
+        MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_b, c->valid_b.as<uint32_t>(), sg2));
+        MP_CUDA_TRY(cudaEventRecord(b->ev_sort_b, sg2));
+        MP_CUDA_TRY(cudaEventRecord(b->ev_g2_acc0, sg2));
+        MP_TRY(msm_accumulate_g2(g2, 1, cnt, sg2));
+        MP_CUDA_TRY(cudaEventRecord(b->ev_g2_acc1, sg2));
+        MP_TRY(msm_reduce_g2(g2, 1, cnt, sg2));
+        MP_CUDA_TRY(cudaEventRecord(b->ev_g2, sg2));
+        return MP_OK;
+    };
+    if (b->overlap) {
+        MP_CUDA_TRY(cudaStreamWaitEvent(sg2, b->ev_z, 0));
+        MP_TRY(g2_path());
+    }
     MP_TRY(r1cs_eval(c->r1cs, b->z_mont.p, c->zlen, cnt, c->m, b->abc.p, st));
     launches += 2;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_WITNESS_MAP], st));
     MP_TRY(witness_map_run(c->dom, b->abc.p, b->s1.p, b->s2.p, cnt, b->h_canon.p, c->m, st));
     launches += (c->log_m > 10 ? 6 : 3) + 1;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_SORT], st));
-    MP_TRY(msm_sort(c->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_z, st));
-    MP_TRY(msm_sort(c->gh, b->h_canon.as<uint32_t>(), (size_t)c->m * 8, cnt, b->sort_h, st));
-    launches += 6;
+    MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_a, c->valid_a.as<uint32_t>(), st));
+    MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_l, c->valid_l.as<uint32_t>(), st));
+    MP_TRY(msm_sort(b->gh, b->h_canon.as<uint32_t>(), (size_t)c->m * 8, cnt, b->sort_h, c->valid_h.as<uint32_t>(), st));
+    launches += 12;
+    if (!b->overlap) {
+        MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_b, c->valid_b.as<uint32_t>(), st));
+    } else {
+        MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_sort_b, 0));  // the B1 job of the G1 launch reads the B list
+    }
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_ACC_G1], st));
-    MsmTables tz{}, th{}, t2{};
-    tz.n_msm = 3;
-    tz.table[0] = c->tab_a.p;  tz.partial[0] = b->part_a.p;  tz.result[0] = b->res_g1.as<char>();
-    tz.table[1] = c->tab_b1.p; tz.partial[1] = b->part_b1.p; tz.result[1] = b->res_g1.as<char>() + cnt * g1w;
-    tz.table[2] = c->tab_l.p;  tz.partial[2] = b->part_l.p;  tz.result[2] = b->res_g1.as<char>() + 2 * cnt * g1w;
-    th.n_msm = 1;
-    th.table[0] = c->tab_h.p;  th.partial[0] = b->part_h.p;  th.result[0] = b->res_g1.as<char>() + 3 * cnt * g1w;
-    t2.n_msm = 1;
-    t2.table[0] = c->tab_b2.p; t2.partial[0] = b->part_b2.p; t2.result[0] = b->res_g2.p;
-    MP_TRY(msm_accumulate_g1(c->gz, b->sort_z, tz, cnt, st));
-    MP_TRY(msm_accumulate_g1(c->gh, b->sort_h, th, cnt, st));
-    launches += 2;
+    MP_TRY(msm_accumulate_g1(g1, 4, cnt, st));
+    launches += 1;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_ACC_G2], st));
-    MP_TRY(msm_accumulate_g2(c->gz, b->sort_z, t2, cnt, st));
+    if (!b->overlap) {
+        MP_CUDA_TRY(cudaEventRecord(b->ev_g2_acc0, st));
+        MP_TRY(msm_accumulate_g2(g2, 1, cnt, st));
+        MP_CUDA_TRY(cudaEventRecord(b->ev_g2_acc1, st));
+    }
     launches += 1;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_REDUCE], st));
-    MP_TRY(msm_reduce_g1(c->gz, b->sort_z, tz, cnt, b->red_scratch_g1.p, st));
-    MP_TRY(msm_reduce_g1(c->gh, b->sort_h, th, cnt, b->red_scratch_g1.p, st));
-    MP_TRY(msm_reduce_g2(c->gz, b->sort_z, t2, cnt, b->red_scratch_g2.p, st));
-    launches += 9;
+    MP_TRY(msm_reduce_g1(g1, 4, cnt, st));
+    if (!b->overlap) MP_TRY(msm_reduce_g2(g2, 1, cnt, st));
+    else MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_g2, 0));
+    launches += 4;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_FINISH], st));
     k_prove_finish<<<(unsigned)cnt, 96, 0, st>>>(b->res_g1.as<XYZZ<Fq>>(), b->res_g2.as<XYZZ<Fq2>>(), b->rs.as<uint32_t>(),
                                                  (uint32_t)cnt, b->proofs.as<uint8_t>());
@@ -328,11 +369,15 @@ static int batch_run_impl(mp_batch* b, float* out_ms) {
     launches += 1;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_COUNT], st));
     MP_CUDA_TRY(cudaStreamSynchronize(st));
+    if (b->overlap) MP_CUDA_TRY(cudaStreamSynchronize(sg2));
     float total = 0;
     for (int ph = PH_PREP; ph < PH_COUNT; ph++) {
         MP_CUDA_TRY(cudaEventElapsedTime(&b->phase_ms[ph], b->ev[ph], b->ev[ph + 1]));
         total += b->phase_ms[ph];
     }
+    // the G2 accumulate always reports its own event pair (it runs beside the other phases when overlapped)
+    MP_CUDA_TRY(cudaEventElapsedTime(&b->phase_ms[PH_ACC_G2], b->ev_g2_acc0, b->ev_g2_acc1));
+    MP_CUDA_TRY(cudaEventElapsedTime(&total, b->ev[PH_PREP], b->ev[PH_COUNT]));
     b->launches = launches;
     b->ran = true;
     if (out_ms) *out_ms = total;
@@ -427,7 +472,10 @@ void mp_batch_destroy(mp_batch* b) {
     if (b->ctx) cudaSetDevice(b->ctx->device);
     for (auto& e : b->ev)
         if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {b->ev_z, b->ev_sort_b, b->ev_g2, b->ev_g2_acc0, b->ev_g2_acc1})
+        if (e) cudaEventDestroy(e);
     if (b->st) cudaStreamDestroy(b->st);
+    if (b->st2) cudaStreamDestroy(b->st2);
     delete b;
 }
 
@@ -473,6 +521,12 @@ int mp_batch_phase_ms(const mp_batch* b, float* out_ms, int max_phases) {
 const char* mp_phase_name(int i) { return (i >= 0 && i < PH_COUNT) ? kPhaseNames[i] : ""; }
 
 uint64_t mp_batch_kernel_launches(const mp_batch* b) { return b ? b->launches : 0; }
+
+int mp_batch_set_overlap(mp_batch* b, int overlap) {
+    if (!b) return MP_ERR_INVALID_ARG;
+    b->overlap = overlap != 0;
+    return MP_OK;
+}
 
 int mp_prove_batch(mp_ctx* ctx, size_t count, const uint64_t* z, const uint64_t* r, const uint64_t* s, uint8_t* out_proofs) {
     if (!ctx) return MP_ERR_INVALID_ARG;
