@@ -51,6 +51,9 @@ def shard_indices(total: int, rank: int, world: int):
     return list(range(rank, total, world))
 
 
+_GATHER_PERM = {}
+
+
 def gather_proofs(local, total: int, rank: int, world: int, device="cuda"):
     """Gather [len(shard), 192] uint8 proof bytes from every rank to rank 0 in global proof order."""
     import torch
@@ -64,12 +67,13 @@ def gather_proofs(local, total: int, rank: int, world: int, device="cuda"):
     dist.all_gather(bufs, padded)
     if rank != 0:
         return None
-    out = torch.empty((total, 192), dtype=torch.uint8, device=device)
-    for r in range(world):
-        idx = shard_indices(total, r, world)
-        if idx:
-            out[torch.tensor(idx, device=device)] = bufs[r][: len(idx)]
-    return out
+    key = (total, world, str(device))
+    perm = _GATHER_PERM.get(key)
+    if perm is None:
+        # global proof i lives at row (i mod world) * per + i div world of the rank-major stack
+        perm = torch.tensor([(i % world) * per + i // world for i in range(total)], device=device)
+        _GATHER_PERM[key] = perm
+    return torch.cat(bufs, dim=0)[perm]
 
 
 def max_over_ranks(x: float, device="cuda") -> float:
@@ -329,7 +333,7 @@ def main():
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"kernel": "k_msm_accumulate<Fq> (G1 bucket accumulation, 2 launches per step)", "bound": "integer-pipe",
+    roofline = {"kernel": "k_msm_accumulate<Fq> (G1 bucket accumulation: A, B1, L, H in one launch per step)", "bound": "integer-pipe",
                 "achieved": achieved, "peak": peak_fq / 1e9, "unit": "GFq-mul/s (credited: pairs x 20 windows x 11, SURVEY 8d)",
                 "frac": (achieved / (peak_fq / 1e9)) if achieved else None, "traffic": traffic,
                 "peak_source": "IMAD.WIDE.U32 issue rate measured live (mp_debug_int_pipe_rate) / 300 per 381-bit Montgomery product",
