@@ -26,11 +26,20 @@ MsmGeom msm_geom(int c, int groups, uint32_t n_scalars, uint32_t table_stride, s
     g.bpg = 1u << (c - 1);
     g.n_buckets = g.bpg * groups;
     g.max_entries = n_scalars * (uint32_t)g.windows;
-    g.max_items = g.n_buckets + g.max_entries / MSM_SEG + 1;
-    // Reduction level 1 is throughput work (2 adds per bucket); its chunk only sets how many threads share it.
-    // Large batches already fill the GPU, so they take long chunks, which shortens the latency-bound level 2.
-    size_t par = (size_t)groups * std::max<size_t>(batch_hint, 1);
-    g.red_s1 = par >= 16 ? 128 : (par >= 4 ? 32 : 8);
+    // slice length: ~2x the mean bucket load, so that uniform inputs give one slice per bucket and only skewed
+    // buckets are split
+    g.seg = 64;
+    while (g.seg < 4096 && (uint64_t)g.seg * g.n_buckets < 2ull * g.max_entries) g.seg *= 2;
+    g.max_items = g.n_buckets + g.max_entries / g.seg + 1;
+    g.max_heavy = g.max_entries / (g.seg * (MSM_HEAVY_SEGS - 1)) + 1;
+    // Reduction level 1 is throughput work (2 adds per bucket); its chunk length only sets how many threads share
+    // it.  Aim at >= ~64k threads per launch (148 SMs x a few hundred resident threads); `batch_hint` counts the
+    // (job x vector) instances that share the launch.  Longer chunks shorten the latency-bound level 2.
+    size_t inst = std::max<size_t>(batch_hint, 1) * (size_t)groups;
+    size_t want = 65536;
+    size_t s1 = (size_t)g.bpg * inst / want;
+    g.red_s1 = 8;
+    while (g.red_s1 * 2 <= s1 && g.red_s1 < 128) g.red_s1 *= 2;
     if (g.red_s1 > g.bpg) g.red_s1 = g.bpg;
     g.l1pg = (g.bpg + g.red_s1 - 1) / g.red_s1;
     g.red_d = 1;
@@ -47,6 +56,8 @@ size_t MsmSortWs::bytes(const MsmGeom& g, size_t batch) const {
     b += align256(batch * (size_t)g.max_items * 8);      // items
     b += align256(batch * 4);                            // n_items
     b += align256(batch * (size_t)g.max_entries * 4);    // entries
+    b += align256(batch * (size_t)g.max_heavy * 4);      // heavy
+    b += align256(batch * 4);                            // n_heavy
     return b;
 }
 
@@ -61,6 +72,8 @@ int msm_sort_ws_alloc(MsmSortWs& ws, const MsmGeom& g, size_t batch, DevBuf& bac
     ws.items = (uint32_t*)take(batch * (size_t)g.max_items * 8);
     ws.n_items = (uint32_t*)take(batch * 4);
     ws.entries = (uint32_t*)take(batch * (size_t)g.max_entries * 4);
+    ws.heavy = (uint32_t*)take(batch * (size_t)g.max_heavy * 4);
+    ws.n_heavy = (uint32_t*)take(batch * 4);
     return MP_OK;
 }
 
@@ -130,9 +143,13 @@ __global__ void k_msm_scatter(MsmGeom g, const uint32_t* __restrict__ scalars, s
 // work-item list ordered by descending segment length, so that the lanes of a warp run equally long loops.
 constexpr int PLAN_THREADS = 1024;
 __global__ void __launch_bounds__(PLAN_THREADS) k_msm_plan(MsmGeom g, const uint32_t* __restrict__ cnt, uint32_t* start,
-                                                          uint32_t* slot_base, uint2* items, uint32_t* n_items) {
+                                                          uint32_t* slot_base, uint2* items, uint32_t* n_items, uint32_t* heavy,
+                                                          uint32_t* n_heavy) {
     __shared__ uint32_t sh_e[PLAN_THREADS], sh_s[PLAN_THREADS];
-    __shared__ uint32_t cls[MSM_SEG + 1];
+    __shared__ uint32_t cls[MSM_CLASSES + 1];
+    const uint32_t SEG = g.seg;
+    // class of a slice of `len` entries: 0 for full slices, up to MSM_CLASSES - 1 for the shortest
+    auto cls_of = [&](uint32_t len) { return (uint32_t)MSM_CLASSES - (uint32_t)(((uint64_t)len * MSM_CLASSES + SEG - 1) / SEG); };
     const uint32_t b = blockIdx.x, tid = threadIdx.x;
     const uint32_t* c = cnt + (size_t)b * g.n_buckets;
     uint32_t* st = start + (size_t)b * g.n_buckets;
@@ -140,12 +157,15 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_msm_plan(MsmGeom g, const uint
     uint2* it = items + (size_t)b * g.max_items;
     const uint32_t per = (g.n_buckets + PLAN_THREADS - 1) / PLAN_THREADS;
     const uint32_t k0 = tid * per, k1 = min(k0 + per, g.n_buckets);
-    if (tid <= MSM_SEG) cls[tid] = 0;
+    if (tid <= MSM_CLASSES) cls[tid] = 0;
+    __shared__ uint32_t sh_heavy;
+    if (tid == 0) sh_heavy = 0;
+    uint32_t* hv = heavy + (size_t)b * g.max_heavy;
     uint32_t se = 0, ss = 0;
     for (uint32_t k = k0; k < k1; k++) {
         uint32_t v = c[k];
         se += v;
-        ss += (v + MSM_SEG - 1) / MSM_SEG;
+        ss += (v + SEG - 1) / SEG;
     }
     sh_e[tid] = se;
     sh_s[tid] = ss;
@@ -165,19 +185,21 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_msm_plan(MsmGeom g, const uint
         st[k] = oe;
         sb[k] = os;
         oe += v;
-        uint32_t full = v / MSM_SEG, rem = v % MSM_SEG;
+        uint32_t full = v / SEG, rem = v % SEG;
         os += full + (rem ? 1 : 0);
         if (full) atomicAdd(&cls[0], full);
-        if (rem) atomicAdd(&cls[MSM_SEG - rem], 1u);
+        if (rem) atomicAdd(&cls[cls_of(rem)], 1u);
+        if (full + (rem ? 1 : 0) >= (uint32_t)MSM_HEAVY_SEGS) hv[atomicAdd(&sh_heavy, 1u)] = k;
     }
     if (tid == PLAN_THREADS - 1) {
         sb[g.n_buckets] = sh_s[tid];
         n_items[b] = sh_s[tid];
     }
     __syncthreads();
+    if (tid == 0) n_heavy[b] = sh_heavy;
     if (tid == 0) {  // exclusive scan over the length classes (class 0 = full segments first)
         uint32_t run = 0;
-        for (int q = 0; q < MSM_SEG; q++) {
+        for (int q = 0; q < MSM_CLASSES; q++) {
             uint32_t v = cls[q];
             cls[q] = run;
             run += v;
@@ -186,13 +208,13 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_msm_plan(MsmGeom g, const uint
     __syncthreads();
     for (uint32_t k = k0; k < k1; k++) {
         uint32_t v = c[k];
-        uint32_t full = v / MSM_SEG, rem = v % MSM_SEG;
+        uint32_t full = v / SEG, rem = v % SEG;
         if (full) {
             uint32_t pos = atomicAdd(&cls[0], full);
             for (uint32_t sidx = 0; sidx < full; sidx++) it[pos + sidx] = make_uint2(k, sidx);
         }
         if (rem) {
-            uint32_t pos = atomicAdd(&cls[MSM_SEG - rem], 1u);
+            uint32_t pos = atomicAdd(&cls[cls_of(rem)], 1u);
             it[pos] = make_uint2(k, full);
         }
     }
@@ -206,7 +228,7 @@ int msm_sort(const MsmGeom& g, const uint32_t* scalars, size_t stride_words, siz
     dim3 grid(div_up(g.n_scalars, 256), (unsigned)batch);
     k_msm_hist<<<grid, 256, 0, st>>>(g, scalars, stride_words, valid, ws.cnt);
     MP_KERNEL_CHECK();
-    k_msm_plan<<<(unsigned)batch, PLAN_THREADS, 0, st>>>(g, ws.cnt, ws.start, ws.slot_base, (uint2*)ws.items, ws.n_items);
+    k_msm_plan<<<(unsigned)batch, PLAN_THREADS, 0, st>>>(g, ws.cnt, ws.start, ws.slot_base, (uint2*)ws.items, ws.n_items, ws.heavy, ws.n_heavy);
     MP_KERNEL_CHECK();
     k_msm_scatter<<<grid, 256, 0, st>>>(g, scalars, stride_words, valid, ws.start, ws.fill, ws.entries);
     MP_KERNEL_CHECK();
@@ -214,11 +236,11 @@ int msm_sort(const MsmGeom& g, const uint32_t* scalars, size_t stride_words, siz
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// bucket accumulation: one thread per work item (a bucket, or a <= MSM_SEG slice of a large bucket)
+// bucket accumulation: one thread per work item (a bucket, or a <= g.seg slice of a large bucket)
 // ---------------------------------------------------------------------------------------------------------
 struct JobDev {
     MsmGeom g;
-    const uint32_t *cnt, *start, *slot_base, *n_items, *entries;
+    const uint32_t *cnt, *start, *slot_base, *n_items, *entries, *heavy, *n_heavy;
     const uint2* items;
     const void* table;
     void* partial;
@@ -237,6 +259,8 @@ static JobsArg make_jobs(const MsmJob* jobs, int n) {
         a.j[i].slot_base = jobs[i].ws.slot_base;
         a.j[i].n_items = jobs[i].ws.n_items;
         a.j[i].entries = jobs[i].ws.entries;
+        a.j[i].heavy = jobs[i].ws.heavy;
+        a.j[i].n_heavy = jobs[i].ws.n_heavy;
         a.j[i].items = (const uint2*)jobs[i].ws.items;
         a.j[i].table = jobs[i].table;
         a.j[i].partial = jobs[i].partial;
@@ -256,8 +280,8 @@ __global__ void __launch_bounds__(THREADS) k_msm_accumulate(const __grid_constan
     const uint2 item = J.items[(size_t)b * g.max_items + j];
     const uint32_t k = item.x, seg = item.y;
     const uint32_t total = J.cnt[(size_t)b * g.n_buckets + k];
-    const uint32_t len = min((uint32_t)MSM_SEG, total - seg * MSM_SEG);
-    const uint32_t* en = J.entries + (size_t)b * g.max_entries + J.start[(size_t)b * g.n_buckets + k] + seg * MSM_SEG;
+    const uint32_t len = min(g.seg, total - seg * g.seg);
+    const uint32_t* en = J.entries + (size_t)b * g.max_entries + J.start[(size_t)b * g.n_buckets + k] + seg * g.seg;
     const uint32_t slot = J.slot_base[(size_t)b * (g.n_buckets + 1) + k] + seg;
     const uint32_t* tab = reinterpret_cast<const uint32_t*>(J.table);
     constexpr int AW = Affine<F>::WORDS;
@@ -272,6 +296,47 @@ __global__ void __launch_bounds__(THREADS) k_msm_accumulate(const __grid_constan
     acc.store(out);
 }
 
+// Buckets that were split into several slices leave one partial sum per slice.  One warp folds such a bucket:
+// lanes stride over its slots, then a shuffle tree adds the 32 lane sums; the total lands in the first slot and the
+// others are reset to infinity, so the reduction sees a single partial per bucket.
+template <class T>
+MP_DEV T shfl_down_words(const T& v, int off) {
+    T r;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&v);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(T) / 4); k++) dst[k] = __shfl_down_sync(0xffffffffu, src[k], off);
+    return r;
+}
+
+constexpr int FOLD_WARPS_PER_BLOCK = 4, FOLD_BLOCKS = 16;
+template <class F>
+__global__ void __launch_bounds__(FOLD_WARPS_PER_BLOCK * 32) k_msm_fold(const __grid_constant__ JobsArg jobs) {
+    const JobDev& J = jobs.j[blockIdx.z];
+    const MsmGeom& g = J.g;
+    const uint32_t b = blockIdx.y, lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * FOLD_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const uint32_t nh = J.n_heavy[b];
+    const uint32_t* hv = J.heavy + (size_t)b * g.max_heavy;
+    const uint32_t* sb = J.slot_base + (size_t)b * (g.n_buckets + 1);
+    XYZZ<F>* part = reinterpret_cast<XYZZ<F>*>(J.partial) + (size_t)b * g.max_items;
+    for (uint32_t h = warp; h < nh; h += FOLD_BLOCKS * FOLD_WARPS_PER_BLOCK) {
+        const uint32_t k = hv[h];
+        const uint32_t s0 = sb[k], s1 = sb[k + 1];
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t s = s0 + lane; s < s1; s += 32) acc = acc.add(XYZZ<F>::load(part + s));
+        for (int off = 16; off >= 1; off >>= 1) {
+            XYZZ<F> other = shfl_down_words(acc, off);
+            acc = acc.add(other);
+        }
+        __syncwarp();
+        for (uint32_t s = s0 + lane; s < s1; s += 32) {
+            if (s == s0) acc.store(part + s);          // lane 0 holds the total
+            else XYZZ<F>::inf().store(part + s);
+        }
+    }
+}
+
 template <class F>
 static int accumulate_impl(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_t st) {
     if (batch == 0 || n_jobs == 0) return MP_OK;
@@ -282,6 +347,8 @@ static int accumulate_impl(const MsmJob* jobs, int n_jobs, size_t batch, cudaStr
     for (int i = 0; i < n_jobs; i++) max_items = std::max(max_items, jobs[i].g.max_items);
     dim3 grid(div_up(max_items, THREADS), (unsigned)batch, (unsigned)n_jobs);
     k_msm_accumulate<F, THREADS><<<grid, THREADS, 0, st>>>(a);
+    MP_KERNEL_CHECK();
+    k_msm_fold<F><<<dim3(FOLD_BLOCKS, (unsigned)batch, (unsigned)n_jobs), FOLD_WARPS_PER_BLOCK * 32, 0, st>>>(a);
     MP_KERNEL_CHECK();
     return MP_OK;
 }
@@ -296,7 +363,7 @@ int msm_accumulate_g2(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_t
 //            total = sum_t a_t + red_s1 * sum_t t s_t
 // scratch per (vector, group): [l1pg][2] level-1 results, then [D][3] (R, C, VA), then [3] partial totals
 // ---------------------------------------------------------------------------------------------------------
-MP_DEV size_t red_words_per_group(const MsmGeom& g) { return (size_t)g.l1pg * 2 + (size_t)g.red_d * 3 + 3; }
+MP_DEV size_t red_words_per_group(const MsmGeom& g) { return max((size_t)g.l1pg * 2, (size_t)32) + (size_t)g.red_d * 3 + 3; }
 
 template <class F>
 MP_DEV XYZZ<F>* red_scratch(const JobDev& J, uint32_t b, uint32_t grp) {
@@ -334,61 +401,69 @@ MP_DEV XYZZ<F> dbl_n(XYZZ<F> p, int n) {
     return p;
 }
 
-// blockIdx.x = vector * groups + group, blockIdx.y = job; blockDim.x >= max(red_d, 3)
+// blockIdx.x = vector * groups + group, blockIdx.y = job; blockDim.x = 3 * max red_d (>= 32)
+// phase 1: 3D threads: row sums R_hi, column sums C_lo of s, row sums VA_hi of a            (D serial adds)
+// phase 2: weighted sums by bit decomposition: sum_q q X_q = sum_b 2^b sum_{q: bit b} X_q     (D/2 serial adds)
+// phase 3: Horner over the bits (log D doublings), VA total; phase 4: combine                   (~ 2 log D + 14)
 template <class F>
-__global__ void __launch_bounds__(64) k_msm_reduce2(const __grid_constant__ JobsArg jobs, uint32_t batch) {
+__global__ void __launch_bounds__(192) k_msm_reduce2(const __grid_constant__ JobsArg jobs, uint32_t batch) {
     const JobDev& J = jobs.j[blockIdx.y];
     const MsmGeom& g = J.g;
     if (blockIdx.x >= batch * g.groups) return;
     const uint32_t b = blockIdx.x / g.groups, grp = blockIdx.x % g.groups;
     const uint32_t D = g.red_d, tid = threadIdx.x;
+    uint32_t LB = 0;
+    while ((1u << LB) < D) LB++;
     XYZZ<F>* sc = red_scratch<F>(J, b, grp);
-    XYZZ<F>* rcv = sc + (size_t)g.l1pg * 2;      // [D][3]
+    XYZZ<F>* rcv = sc + max((size_t)g.l1pg * 2, (size_t)32);  // [D][3]: R, C, VA
     XYZZ<F>* tot = rcv + (size_t)D * 3;          // [3]
-    if (tid < D) {
-        XYZZ<F> R = XYZZ<F>::inf(), C = XYZZ<F>::inf(), VA = XYZZ<F>::inf();
+    // scratch for phase 2 lives behind the level-1 results that phase 1 has consumed: sc[0 .. 2*LB + 4)
+    if (tid < 3 * D) {
+        const uint32_t kind = tid / D, idx = tid % D;
+        XYZZ<F> acc = XYZZ<F>::inf();
         for (uint32_t q = 0; q < D; q++) {
-            uint32_t tr = tid * D + q;   // row tid
-            if (tr < g.l1pg) {
-                R = R.add(XYZZ<F>::load(sc + (size_t)tr * 2));
-                VA = VA.add(XYZZ<F>::load(sc + (size_t)tr * 2 + 1));
-            }
-            uint32_t tc = q * D + tid;   // column tid
-            if (tc < g.l1pg) C = C.add(XYZZ<F>::load(sc + (size_t)tc * 2));
+            uint32_t t = (kind == 1) ? q * D + idx : idx * D + q;   // column idx | row idx
+            if (t < g.l1pg) acc = acc.add(XYZZ<F>::load(sc + (size_t)t * 2 + (kind == 2 ? 1 : 0)));
         }
-        R.store(rcv + (size_t)tid * 3);
-        C.store(rcv + (size_t)tid * 3 + 1);
-        VA.store(rcv + (size_t)tid * 3 + 2);
+        acc.store(rcv + (size_t)idx * 3 + kind);
     }
     __syncthreads();
-    if (tid < 3) {
-        // tid 0: sum_hi hi R_hi, tid 1: sum_lo lo C_lo (running sums from the top), tid 2: sum VA
-        XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
-        if (tid == 2) {
-            for (uint32_t q = 0; q < D; q++) acc = acc.add(XYZZ<F>::load(rcv + (size_t)q * 3 + 2));
-        } else {
-            for (int q = (int)D - 1; q >= 1; q--) {
-                run = run.add(XYZZ<F>::load(rcv + (size_t)q * 3 + tid));
-                acc = acc.add(run);
-            }
-        }
+    XYZZ<F>* bits = sc;  // [2][LB] bit sums, then [4] VA partials  (needs 2*LB + 4 <= 2 * l1pg, checked on the host)
+    if (tid < 2 * LB) {
+        const uint32_t w = tid / LB, bit = tid % LB;
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t q = 0; q < D; q++)
+            if ((q >> bit) & 1) acc = acc.add(XYZZ<F>::load(rcv + (size_t)q * 3 + w));
+        acc.store(bits + tid);
+    } else if (tid < 2 * LB + 4) {
+        const uint32_t part = tid - 2 * LB;
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t q = part; q < D; q += 4) acc = acc.add(XYZZ<F>::load(rcv + (size_t)q * 3 + 2));
+        acc.store(bits + tid);
+    }
+    __syncthreads();
+    if (tid < 2) {
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (int bit = (int)LB - 1; bit >= 0; bit--) acc = acc.dbl().add(XYZZ<F>::load(bits + tid * LB + bit));
         acc.store(tot + tid);
+    } else if (tid == 2) {
+        XYZZ<F> acc = XYZZ<F>::load(bits + 2 * LB);
+        for (int k = 1; k < 4; k++) acc = acc.add(XYZZ<F>::load(bits + 2 * LB + k));
+        acc.store(tot + 2);
     }
     __syncthreads();
     if (tid == 0) {
-        int ld = 0, ls = 0;
-        while ((1u << ld) < D) ld++;
+        uint32_t ls = 0;
         while ((1u << ls) < g.red_s1) ls++;
-        XYZZ<F> T = dbl_n(XYZZ<F>::load(tot), ld).add(XYZZ<F>::load(tot + 1));
-        // red_s1 is a power of two unless it was clamped to bpg (also a power of two)
-        T = dbl_n(T, ls).add(XYZZ<F>::load(tot + 2));
+        XYZZ<F> T = dbl_n(XYZZ<F>::load(tot), (int)LB).add(XYZZ<F>::load(tot + 1));
+        T = dbl_n(T, (int)ls).add(XYZZ<F>::load(tot + 2));
         T.store(reinterpret_cast<XYZZ<F>*>(J.result) + (size_t)b * g.groups + grp);
     }
 }
 
 size_t msm_reduce_scratch_bytes(const MsmGeom& g, size_t batch, bool g2) {
     size_t words = g2 ? XYZZ<Fq2>::WORDS : XYZZ<Fq>::WORDS;
-    size_t per_group = (size_t)g.l1pg * 2 + (size_t)g.red_d * 3 + 3;
+    size_t per_group = std::max<size_t>((size_t)g.l1pg * 2, 32) + (size_t)g.red_d * 3 + 3;
     return batch * g.groups * per_group * words * 4;
 }
 
@@ -406,7 +481,7 @@ static int reduce_impl(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_
     if (max_d > 64) { set_error_detail("msm reduce: level-2 grid %u exceeds 64", max_d); return MP_ERR_UNSUPPORTED; }
     k_msm_reduce1<F><<<dim3(div_up(max_chunks, 64), (unsigned)batch, (unsigned)n_jobs), 64, 0, st>>>(a);
     MP_KERNEL_CHECK();
-    unsigned th = std::max(32u, max_d);
+    unsigned th = std::max(32u, 3 * max_d);
     k_msm_reduce2<F><<<dim3(max_bg, (unsigned)n_jobs), th, 0, st>>>(a, (uint32_t)batch);
     MP_KERNEL_CHECK();
     return MP_OK;

@@ -11,8 +11,9 @@
 
 namespace mp {
 
-constexpr int MSM_SEG = 64;            // max entries one thread accumulates (large buckets are split)
+constexpr int MSM_CLASSES = 64;        // length classes used to order work items (longest first)
 constexpr int MSM_MAX_JOBS = 4;        // MSMs handled by one accumulate / reduce launch
+constexpr int MSM_HEAVY_SEGS = 33;     // buckets with this many slices or more are folded by a whole warp
 
 struct MsmGeom {
     int c;            // window bits (2..16)
@@ -24,7 +25,9 @@ struct MsmGeom {
     uint32_t bpg;            // buckets per group = 2^(c-1)
     uint32_t n_buckets;      // groups * bpg
     uint32_t max_entries;    // n_scalars * windows
-    uint32_t max_items;      // n_buckets + max_entries / MSM_SEG + 1
+    uint32_t seg;            // max entries one thread accumulates (power of two >= 64, ~2x the mean bucket load)
+    uint32_t max_items;      // n_buckets + max_entries / seg + 1
+    uint32_t max_heavy;      // max_entries / (seg * (MSM_HEAVY_SEGS - 1)) + 1
     uint32_t red_s1;         // buckets per thread in reduction level 1
     uint32_t l1pg;           // level-1 chunks per group = ceil(bpg / red_s1)
     uint32_t red_d;          // level 2 works on a red_d x red_d grid of level-1 chunks (power of two, red_d^2 >= l1pg)
@@ -41,6 +44,8 @@ struct MsmSortWs {
     uint32_t* items = nullptr;      // [batch][max_items]   work items (bucket, segment), longest first
     uint32_t* n_items = nullptr;    // [batch]
     uint32_t* entries = nullptr;    // [batch][max_entries] sorted (sign << 31 | table index)
+    uint32_t* heavy = nullptr;      // [batch][max_heavy]   buckets split into >= MSM_HEAVY_SEGS slices
+    uint32_t* n_heavy = nullptr;    // [batch]
     size_t bytes(const MsmGeom& g, size_t batch) const;
 };
 int msm_sort_ws_alloc(MsmSortWs& ws, const MsmGeom& g, size_t batch, DevBuf& backing);

@@ -272,8 +272,8 @@ static int batch_create_impl(mp_ctx* c, size_t cap, mp_batch* b) {
     MP_TRY(b->s1.alloc(cap * 3 * m * 32));
     MP_TRY(b->s2.alloc(cap * 3 * m * 32));
     MP_TRY(b->h_canon.alloc(cap * m * 32));
-    b->gz = msm_geom(PROVE_C, 1, c->zlen, c->zlen, cap);
-    b->gh = msm_geom(PROVE_C, 1, (uint32_t)c->m, (uint32_t)c->m, cap);
+    b->gz = msm_geom(PROVE_C, 1, c->zlen, c->zlen, cap * 2);  // G1 launches carry 4 jobs, the G2 launch one
+    b->gh = msm_geom(PROVE_C, 1, (uint32_t)c->m, (uint32_t)c->m, cap * 2);
     MP_TRY(msm_sort_ws_alloc(b->sort_a, b->gz, cap, b->sort_a_mem));
     MP_TRY(msm_sort_ws_alloc(b->sort_b, b->gz, cap, b->sort_b_mem));
     MP_TRY(msm_sort_ws_alloc(b->sort_l, b->gz, cap, b->sort_l_mem));
@@ -349,14 +349,14 @@ static int batch_run_impl(mp_batch* b, float* out_ms) {
     }
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_ACC_G1], st));
     MP_TRY(msm_accumulate_g1(g1, 4, cnt, st));
-    launches += 1;
+    launches += 2;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_ACC_G2], st));
     if (!b->overlap) {
         MP_CUDA_TRY(cudaEventRecord(b->ev_g2_acc0, st));
         MP_TRY(msm_accumulate_g2(g2, 1, cnt, st));
         MP_CUDA_TRY(cudaEventRecord(b->ev_g2_acc1, st));
     }
-    launches += 1;
+    launches += 2;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_REDUCE], st));
     MP_TRY(msm_reduce_g1(g1, 4, cnt, st));
     if (!b->overlap) MP_TRY(msm_reduce_g2(g2, 1, cnt, st));

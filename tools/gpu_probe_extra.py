@@ -32,7 +32,8 @@ if "--latency" in sys.argv:
 if "--sweep" in sys.argv:
     from oracle import cref
     rng = random.Random(1)
-    for logn in (16, 18, 20, 22, 24):
+    sizes = [int(x) for x in os.environ.get('SWEEP', '16,18,20,22,24').split(',')]
+    for logn in sizes:
         n = 1 << logn
         base_k = [rng.randrange(1, wl.FR_BLS12_381) for _ in range(1 << 12)]
         pts = ctypes.create_string_buffer((1 << 12) * 96)
@@ -40,7 +41,8 @@ if "--sweep" in sys.argv:
         reps = n >> 12
         bases = pts.raw * reps                       # repeated bases: closed form still holds
         t0 = time.time()
-        sc_bytes = random.Random(logn).randbytes(n * 32)
+        rr = random.Random(logn)
+        sc_bytes = b''.join(rr.randbytes(1 << 20) for _ in range(n * 32 >> 20)) if n * 32 >= (1 << 20) else rr.randbytes(n * 32)
         sc_arr = bytearray(sc_bytes)
         for i in range(n):                            # clear top bits so that scalars < r
             sc_arr[32 * i + 31] &= 0x3F
