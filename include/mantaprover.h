@@ -107,10 +107,22 @@ MP_API int mp_prove_batch(mp_ctx* ctx, size_t count, const uint64_t* z, const ui
 /* Staged form of mp_prove_batch (what it does internally), so a harness can time the device-resident part:
  * upload = H2D of assignments, run = all kernels, download = D2H of proof bytes. */
 MP_API int mp_batch_create(mp_ctx* ctx, size_t capacity, mp_batch** out);
+/* high_priority = 1 puts the batch's streams at the greatest CUDA stream priority: with two batches in flight the
+ * low-priority one only fills the gaps (latency-bound tails, copies) of the high-priority one. */
+MP_API int mp_batch_create_ex(mp_ctx* ctx, size_t capacity, int high_priority, mp_batch** out);
 MP_API void mp_batch_destroy(mp_batch* b);
 MP_API int mp_batch_upload(mp_batch* b, size_t count, const uint64_t* z, const uint64_t* r, const uint64_t* s);
 MP_API int mp_batch_run(mp_batch* b, float* out_device_ms /* nullable: CUDA-event time of the whole run */);
 MP_API int mp_batch_download(mp_batch* b, uint8_t* out_proofs);
+/* Asynchronous forms, for keeping two batches in flight so that the latency-bound tail of one (bucket-reduction level 2,
+ * finishing kernel) and its host copies hide behind the kernels of the next:
+ *   mp_batch_run_async  = mp_batch_run without the final synchronisation (inputs already uploaded);
+ *   mp_batch_submit     = H2D of the inputs + all kernels + D2H of the proofs into out_proofs, all enqueued; host buffers
+ *                         must stay valid (pinned memory makes the copies truly asynchronous) until mp_batch_wait;
+ *   mp_batch_wait       = block until the batch is done; reports the CUDA-event time of its kernels. */
+MP_API int mp_batch_run_async(mp_batch* b);
+MP_API int mp_batch_submit(mp_batch* b, size_t count, const uint64_t* z, const uint64_t* r, const uint64_t* s, uint8_t* out_proofs);
+MP_API int mp_batch_wait(mp_batch* b, float* out_device_ms);
 /* per-phase CUDA-event times of the last mp_batch_run, in ms; names via mp_phase_name(i). Returns count. */
 MP_API int mp_batch_phase_ms(const mp_batch* b, float* out_ms, int max_phases);
 MP_API const char* mp_phase_name(int i);

@@ -50,10 +50,14 @@ SYMBOLS = {
     "mp_prove": (_I, [_V, _V, _V, _V, _V]),
     "mp_prove_batch": (_I, [_V, _SZ, _V, _V, _V, _V]),
     "mp_batch_create": (_I, [_V, _SZ, _V]),
+    "mp_batch_create_ex": (_I, [_V, _SZ, _I, _V]),
     "mp_batch_destroy": (None, [_V]),
     "mp_batch_upload": (_I, [_V, _SZ, _V, _V, _V]),
     "mp_batch_run": (_I, [_V, _V]),
     "mp_batch_download": (_I, [_V, _V]),
+    "mp_batch_run_async": (_I, [_V]),
+    "mp_batch_submit": (_I, [_V, _SZ, _V, _V, _V, _V]),
+    "mp_batch_wait": (_I, [_V, _V]),
     "mp_batch_phase_ms": (_I, [_V, _V, _I]),
     "mp_phase_name": (ctypes.c_char_p, [_I]),
     "mp_batch_kernel_launches": (ctypes.c_uint64, [_V]),

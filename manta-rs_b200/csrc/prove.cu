@@ -47,6 +47,8 @@ struct mp_ctx {
     DevBuf valid_a, valid_b, valid_l, valid_h;  // per-table "base is not infinity" bitmaps
     size_t device_bytes = 0;
     std::mutex mu;
+    std::mutex single_mu;          // serialises mp_prove callers on the cached one-proof batch
+    mp_batch* single = nullptr;   // lazily created capacity-1 batch behind mp_prove
 };
 
 struct mp_batch {
@@ -64,7 +66,7 @@ struct mp_batch {
     cudaEvent_t ev[PH_COUNT + 1] = {};
     float phase_ms[PH_COUNT] = {};
     uint64_t launches = 0;
-    bool ran = false;
+    bool ran = false, in_flight = false, upload_timed = false;
 };
 
 namespace mp {
@@ -256,12 +258,15 @@ static int ctx_create_impl(const mp_pk_view* pk, const mp_r1cs_view* r1cs, int d
     return MP_OK;
 }
 
-static int batch_create_impl(mp_ctx* c, size_t cap, mp_batch* b) {
+static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch* b) {
     MP_TRY(use_device(c->device));
     b->ctx = c;
     b->capacity = cap;
-    MP_CUDA_TRY(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
-    MP_CUDA_TRY(cudaStreamCreateWithFlags(&b->st2, cudaStreamNonBlocking));
+    int prio_least = 0, prio_greatest = 0;
+    MP_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    const int prio = high_priority ? prio_greatest : prio_least;
+    MP_CUDA_TRY(cudaStreamCreateWithPriority(&b->st, cudaStreamNonBlocking, prio));
+    MP_CUDA_TRY(cudaStreamCreateWithPriority(&b->st2, cudaStreamNonBlocking, prio));
     for (auto& e : b->ev) MP_CUDA_TRY(cudaEventCreate(&e));
     for (cudaEvent_t* e : {&b->ev_z, &b->ev_sort_b, &b->ev_g2, &b->ev_g2_acc0, &b->ev_g2_acc1}) MP_CUDA_TRY(cudaEventCreate(e));
     const size_t m = c->m;
@@ -295,10 +300,11 @@ static int batch_create_impl(mp_ctx* c, size_t cap, mp_batch* b) {
     return MP_OK;
 }
 
-static int batch_run_impl(mp_batch* b, float* out_ms) {
+// Enqueues every kernel of one batch on the batch's streams; returns without synchronising.
+static int batch_enqueue(mp_batch* b) {
     mp_ctx* c = b->ctx;
     const size_t cnt = b->count;
-    if (cnt == 0) { if (out_ms) *out_ms = 0; return MP_OK; }
+    if (cnt == 0) return MP_OK;
     MP_TRY(use_device(c->device));
     cudaStream_t st = b->st;
     uint64_t launches = 0;
@@ -368,17 +374,24 @@ static int batch_run_impl(mp_batch* b, float* out_ms) {
     MP_KERNEL_CHECK();
     launches += 1;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_COUNT], st));
-    MP_CUDA_TRY(cudaStreamSynchronize(st));
-    if (b->overlap) MP_CUDA_TRY(cudaStreamSynchronize(sg2));
+    b->launches = launches;
+    b->in_flight = true;
+    return MP_OK;
+}
+
+// Waits for the batch's streams and collects the CUDA-event times of the run.
+static int batch_finalize(mp_batch* b, float* out_ms) {
+    if (out_ms) *out_ms = 0;
+    if (!b->in_flight) return MP_OK;
+    MP_TRY(use_device(b->ctx->device));
+    MP_CUDA_TRY(cudaStreamSynchronize(b->st));
+    MP_CUDA_TRY(cudaStreamSynchronize(b->st2));
+    b->in_flight = false;
     float total = 0;
-    for (int ph = PH_PREP; ph < PH_COUNT; ph++) {
-        MP_CUDA_TRY(cudaEventElapsedTime(&b->phase_ms[ph], b->ev[ph], b->ev[ph + 1]));
-        total += b->phase_ms[ph];
-    }
+    for (int ph = PH_PREP; ph < PH_COUNT; ph++) MP_CUDA_TRY(cudaEventElapsedTime(&b->phase_ms[ph], b->ev[ph], b->ev[ph + 1]));
     // the G2 accumulate always reports its own event pair (it runs beside the other phases when overlapped)
     MP_CUDA_TRY(cudaEventElapsedTime(&b->phase_ms[PH_ACC_G2], b->ev_g2_acc0, b->ev_g2_acc1));
     MP_CUDA_TRY(cudaEventElapsedTime(&total, b->ev[PH_PREP], b->ev[PH_COUNT]));
-    b->launches = launches;
     b->ran = true;
     if (out_ms) *out_ms = total;
     return MP_OK;
@@ -442,6 +455,7 @@ int mp_ctx_create(const mp_pk_view* pk, const mp_r1cs_view* r1cs, int device, mp
 void mp_ctx_destroy(mp_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->single) mp_batch_destroy(ctx->single);
     delete ctx;
 }
 
@@ -454,11 +468,13 @@ int mp_ctx_info(const mp_ctx* ctx, uint64_t* n_vars, uint64_t* n_instance, uint6
     return MP_OK;
 }
 
-int mp_batch_create(mp_ctx* ctx, size_t capacity, mp_batch** out) {
+int mp_batch_create(mp_ctx* ctx, size_t capacity, mp_batch** out) { return mp_batch_create_ex(ctx, capacity, 0, out); }
+
+int mp_batch_create_ex(mp_ctx* ctx, size_t capacity, int high_priority, mp_batch** out) {
     if (!ctx || !out || capacity == 0 || capacity > 60000) return MP_ERR_INVALID_ARG;
     mp_batch* b = new (std::nothrow) mp_batch();
     if (!b) return MP_ERR_OOM;
-    int rc = batch_create_impl(ctx, capacity, b);
+    int rc = batch_create_impl(ctx, capacity, high_priority, b);
     if (rc != MP_OK) {
         mp_batch_destroy(b);
         return rc;
@@ -470,6 +486,8 @@ int mp_batch_create(mp_ctx* ctx, size_t capacity, mp_batch** out) {
 void mp_batch_destroy(mp_batch* b) {
     if (!b) return;
     if (b->ctx) cudaSetDevice(b->ctx->device);
+    if (b->st) cudaStreamSynchronize(b->st);
+    if (b->st2) cudaStreamSynchronize(b->st2);
     for (auto& e : b->ev)
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : {b->ev_z, b->ev_sort_b, b->ev_g2, b->ev_g2_acc0, b->ev_g2_acc1})
@@ -480,7 +498,7 @@ void mp_batch_destroy(mp_batch* b) {
 }
 
 int mp_batch_upload(mp_batch* b, size_t count, const uint64_t* z, const uint64_t* r, const uint64_t* s) {
-    if (!b || count > b->capacity || (count && (!z || !r || !s))) return MP_ERR_INVALID_ARG;
+    if (!b || b->in_flight || count > b->capacity || (count && (!z || !r || !s))) return MP_ERR_INVALID_ARG;
     mp_ctx* c = b->ctx;
     MP_TRY(use_device(c->device));
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_UPLOAD], b->st));
@@ -499,12 +517,40 @@ int mp_batch_upload(mp_batch* b, size_t count, const uint64_t* z, const uint64_t
 
 int mp_batch_run(mp_batch* b, float* out_device_ms) {
     if (!b) return MP_ERR_INVALID_ARG;
+    MP_TRY(mp_batch_run_async(b));
+    return mp_batch_wait(b, out_device_ms);
+}
+
+int mp_batch_run_async(mp_batch* b) {
+    if (!b || b->in_flight) return MP_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(b->ctx->mu);
-    return batch_run_impl(b, out_device_ms);
+    return batch_enqueue(b);
+}
+
+int mp_batch_wait(mp_batch* b, float* out_device_ms) {
+    if (!b) return MP_ERR_INVALID_ARG;
+    return batch_finalize(b, out_device_ms);
+}
+
+int mp_batch_submit(mp_batch* b, size_t count, const uint64_t* z, const uint64_t* r, const uint64_t* s, uint8_t* out_proofs) {
+    if (!b || b->in_flight || count > b->capacity || (count && (!z || !r || !s || !out_proofs))) return MP_ERR_INVALID_ARG;
+    mp_ctx* c = b->ctx;
+    MP_TRY(use_device(c->device));
+    std::lock_guard<std::mutex> lock(c->mu);
+    b->count = count;
+    b->ran = false;
+    if (count == 0) return MP_OK;
+    MP_CUDA_TRY(cudaMemcpy2DAsync(b->z_canon.p, (size_t)c->zlen * 32, z, c->n * 32, c->n * 32, count, cudaMemcpyHostToDevice, b->st));
+    MP_CUDA_TRY(cudaMemcpy2DAsync(b->rs.p, 64, r, 32, 32, count, cudaMemcpyHostToDevice, b->st));
+    MP_CUDA_TRY(cudaMemcpy2DAsync(b->rs.as<char>() + 32, 64, s, 32, 32, count, cudaMemcpyHostToDevice, b->st));
+    MP_TRY(batch_enqueue(b));
+    MP_CUDA_TRY(cudaMemcpyAsync(out_proofs, b->proofs.p, count * MP_PROOF_BYTES, cudaMemcpyDeviceToHost, b->st));
+    return MP_OK;
 }
 
 int mp_batch_download(mp_batch* b, uint8_t* out_proofs) {
     if (!b || (b->count && !out_proofs)) return MP_ERR_INVALID_ARG;
+    if (b->in_flight) MP_TRY(batch_finalize(b, nullptr));
     if (!b->ran && b->count) { mp::set_error_detail("mp_batch_download before mp_batch_run"); return MP_ERR_INVALID_ARG; }
     MP_TRY(use_device(b->ctx->device));
     if (b->count) MP_CUDA_TRY(cudaMemcpy(out_proofs, b->proofs.p, b->count * MP_PROOF_BYTES, cudaMemcpyDeviceToHost));
@@ -541,7 +587,13 @@ int mp_prove_batch(mp_ctx* ctx, size_t count, const uint64_t* z, const uint64_t*
 }
 
 int mp_prove(mp_ctx* ctx, const uint64_t* z, const uint64_t r[4], const uint64_t s[4], uint8_t out_proof[MP_PROOF_BYTES]) {
-    return mp_prove_batch(ctx, 1, z, r, s, out_proof);
+    if (!ctx || !z || !r || !s || !out_proof) return MP_ERR_INVALID_ARG;
+    // one cached capacity-1 batch per context: no allocation on the per-proof path; concurrent callers queue here
+    std::lock_guard<std::mutex> lock(ctx->single_mu);
+    if (!ctx->single) MP_TRY(mp_batch_create(ctx, 1, &ctx->single));
+    MP_TRY(mp_batch_upload(ctx->single, 1, z, r, s));
+    MP_TRY(mp_batch_run(ctx->single, nullptr));
+    return mp_batch_download(ctx->single, out_proof);
 }
 
 int mp_witness_map(mp_ctx* ctx, const uint64_t* z, uint64_t* out_h) {

@@ -262,3 +262,57 @@ def test_msm_closed_form_large(native):
     out = ctypes.create_string_buffer(96)
     _chk(native, native.lib().mp_msm_g1(0, bases, native.pack_scalars(sc), n, out, None))
     assert out.raw == cref.fixed_base(1, [sum(k * s for k, s in zip(ks, sc)) % C.r])
+
+
+def test_batch_api_sync_async_and_serialised(native):
+    """The staged C ABI (upload / run / download), its asynchronous form with two batches in flight
+    (submit / wait) and the serialised single-stream mode all give the oracle's bytes."""
+    from manta_rs_b200 import groth16 as g16
+    lib = native.lib()
+    cs = wl.make_r1cs(4, 500, dist="R")
+    pk, trap = oracle_keygen(cs, wl.sample_trapdoor(12))
+    ctx = g16.ProvingContext.decode(pk)
+    zs = [wl.make_assignment(cs, s) for s in range(6)]
+    rng = random.Random(9)
+    rs = [rng.randrange(C.r) for _ in zs]
+    ss = [rng.randrange(C.r) for _ in zs]
+    expect = [trapdoor_proof_bytes(cs, trap, z, r, s) for z, r, s in zip(zs, rs, ss)]
+    h = ctx.native(g16.R1CS.from_workload(cs, zs[0]).matrices)
+    batches = [ctypes.c_void_p(), ctypes.c_void_p()]
+    for b in batches:
+        _chk(native, lib.mp_batch_create(h, 3, ctypes.byref(b)))
+    pack = lambda lo, hi: (native.pack_scalars([v for z in zs[lo:hi] for v in z]), native.pack_scalars(rs[lo:hi]), native.pack_scalars(ss[lo:hi]))
+    # synchronous staged form, overlapped and serialised
+    for overlap in (1, 0):
+        _chk(native, lib.mp_batch_set_overlap(batches[0], overlap))
+        zb, rb, sb = pack(0, 3)
+        _chk(native, lib.mp_batch_upload(batches[0], 3, zb, rb, sb))
+        ms = ctypes.c_float()
+        _chk(native, lib.mp_batch_run(batches[0], ctypes.byref(ms)))
+        out = ctypes.create_string_buffer(3 * 192)
+        _chk(native, lib.mp_batch_download(batches[0], out))
+        assert [out.raw[i * 192:(i + 1) * 192] for i in range(3)] == expect[0:3]
+        assert ms.value > 0 and lib.mp_batch_kernel_launches(batches[0]) > 10
+    _chk(native, lib.mp_batch_set_overlap(batches[0], 1))
+    # two batches in flight
+    bufs = [pack(0, 3), pack(3, 6)]
+    outs = [ctypes.create_string_buffer(3 * 192), ctypes.create_string_buffer(3 * 192)]
+    for i in range(2):
+        _chk(native, lib.mp_batch_submit(batches[i], 3, bufs[i][0], bufs[i][1], bufs[i][2], outs[i]))
+    # a batch that is in flight refuses new work instead of corrupting it
+    assert lib.mp_batch_run_async(batches[0]) == 1
+    for i in range(2):
+        _chk(native, lib.mp_batch_wait(batches[i], None))
+    assert [outs[0].raw[i * 192:(i + 1) * 192] for i in range(3)] == expect[0:3]
+    assert [outs[1].raw[i * 192:(i + 1) * 192] for i in range(3)] == expect[3:6]
+    # partial batch and empty batch
+    zb, rb, sb = pack(4, 5)
+    _chk(native, lib.mp_batch_upload(batches[1], 1, zb, rb, sb))
+    _chk(native, lib.mp_batch_run(batches[1], None))
+    one = ctypes.create_string_buffer(192)
+    _chk(native, lib.mp_batch_download(batches[1], one))
+    assert one.raw == expect[4]
+    assert lib.mp_batch_upload(batches[1], 4, zb, rb, sb) == 1     # over capacity
+    for b in batches:
+        lib.mp_batch_destroy(b)
+    ctx.close()
