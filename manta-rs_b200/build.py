@@ -28,7 +28,7 @@ def _newest_header():
     t = 0.0
     for d in (CSRC, os.path.join(ROOT, "include")):
         for f in os.listdir(d):
-            if f.endswith((".cuh", ".h")):
+            if f.endswith((".cuh", ".h", ".inc")):
                 t = max(t, os.path.getmtime(os.path.join(d, f)))
     return t
 
