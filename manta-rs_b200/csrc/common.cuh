@@ -31,7 +31,13 @@ void set_error_detail(const char* fmt, ...);
         if (_rc != MP_OK) return _rc; \
     } while (0)
 
-#define MP_KERNEL_CHECK() MP_CUDA_TRY(cudaGetLastError())
+// every kernel launch of the library is followed by this check; it also feeds the per-batch launch count
+uint64_t& kernel_launch_counter();
+#define MP_KERNEL_CHECK()                 \
+    do {                                  \
+        mp::kernel_launch_counter()++;    \
+        MP_CUDA_TRY(cudaGetLastError());  \
+    } while (0)
 
 // Selects the device and verifies it is an sm_100-class part (no fallback path exists).
 int use_device(int device);

@@ -7,6 +7,11 @@ namespace mp {
 
 static thread_local char g_detail[512] = "";
 
+uint64_t& kernel_launch_counter() {
+    static thread_local uint64_t n = 0;
+    return n;
+}
+
 void set_error_detail(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);

@@ -509,6 +509,76 @@ struct Fp {
     }
     MP_DEV Fp inv() const { return pow_const(P::pm2(), P::BITS); }  // 0 -> 0
 
+    // Inversion by the binary extended Euclid: shifts, adds and subtracts only, so it runs on the ALU pipe and leaves
+    // the multiplier pipe (the MSM bottleneck) to the other warps.  ~1.5 * 2 * BITS single-case steps.  0 -> 0.
+    // Invariants (plain integers, a = the Montgomery limbs of *this):  x1 * a == u, x2 * a == v  (mod p).
+    MP_COLD Fp inv_gcd() const {
+        if (is_zero()) return zero();
+        const uint32_t* m = P::mod();
+        uint32_t u[N], v[N], x1[N], x2[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) { u[i] = l[i]; v[i] = m[i]; x1[i] = 0; x2[i] = 0; }
+        x1[0] = 1;
+        auto is_one = [](const uint32_t* a) {
+            uint32_t acc = a[0] ^ 1u;
+#pragma unroll
+            for (int i = 1; i < N; i++) acc |= a[i];
+            return acc == 0;
+        };
+        auto shr1 = [](uint32_t* a) {
+#pragma unroll
+            for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+            a[N - 1] >>= 1;
+        };
+        auto halve_mod = [&](uint32_t* x) {  // x / 2 mod p  (x < p; x + p < 2^(32N))
+            if (x[0] & 1u) {
+                add_cc(x[0], x[0], m[0]);
+#pragma unroll
+                for (int i = 1; i < N - 1; i++) addc_cc(x[i], x[i], m[i]);
+                addc(x[N - 1], x[N - 1], m[N - 1]);
+            }
+            shr1(x);
+        };
+        auto sub_mod = [&](uint32_t* x, const uint32_t* y) {  // x = x - y mod p
+            uint32_t borrow = sub_raw(x, x, y);
+            if (borrow) {
+                add_cc(x[0], x[0], m[0]);
+#pragma unroll
+                for (int i = 1; i < N - 1; i++) addc_cc(x[i], x[i], m[i]);
+                addc(x[N - 1], x[N - 1], m[N - 1]);
+            }
+        };
+        for (int it = 0; it < 4 * 32 * N; it++) {  // bound for safety; terminates long before
+            if (is_one(u) || is_one(v)) break;
+            if (!(u[0] & 1u)) {
+                shr1(u);
+                halve_mod(x1);
+            } else if (!(v[0] & 1u)) {
+                shr1(v);
+                halve_mod(x2);
+            } else {
+                uint32_t t[N];
+                uint32_t borrow = sub_raw(t, u, v);
+                if (!borrow) {  // u >= v
+#pragma unroll
+                    for (int i = 0; i < N; i++) u[i] = t[i];
+                    sub_mod(x1, x2);
+                } else {
+                    sub_raw(v, v, u);
+                    sub_mod(x2, x1);
+                }
+            }
+        }
+        Fp r;
+        const bool pick_u = is_one(u);
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = pick_u ? x1[i] : x2[i];
+        // r = (a R)^-1 as a plain integer = a^-1 R^-1; Montgomery form of a^-1 is a^-1 R = mont_mul(r, R^3)
+        Fp r2 = from_const(P::r2());
+        Fp r3 = r2.mul_cold(r2);
+        return r.mul_cold(r3);
+    }
+
     // canonical (non-Montgomery) integer > (p-1)/2 ?   (ark's `y > -y` flag)
     MP_DEV static bool canonical_gt_half(const Fp& canon) {
         uint32_t t[N];

@@ -1,8 +1,14 @@
 // Internal interface of the bucket-method MSM (msm.cu) used by the stand-alone entry points and by the prover.
 //
 // Replaces ark-ec 0.3 `VariableBaseMSM::multi_scalar_mul`.  Pipeline per scalar list:
-//   digits+histogram -> scan/plan -> scatter (counting sort by bucket) -> bucket accumulate (XYZZ mixed adds)
+//   digits+histogram -> scan/plan -> scatter (counting sort by bucket) -> bucket accumulate
 //   -> 2-level bucket reduction (running sums, then a row/column split of the chunk index) -> (optional) Horner.
+// Bucket accumulation has two implementations:
+//   * batched affine (default): every bucket is summed by a pairwise tree, one round per tree level; all pairs of a
+//     round (every bucket, MSM and proof of the launch) are independent affine additions that share their field
+//     inversion by Montgomery's trick (thread-local prefix products -> 64-way second level -> one binary-Euclid
+//     inversion per 64 threads on the ALU pipe).  6 field multiplications per addition instead of 10.
+//   * XYZZ (MP_MSM_XYZZ=1): one thread per bucket slice, mixed additions into an extended-Jacobian accumulator.
 // Signed c-bit digits: 2^(c-1) buckets per window group.  A "table" holds `rows` precomputed multiples
 // 2^(c*groups*t) * P_i (t < rows) so that window w = t*groups + g lands in bucket set g with point row t;
 // rows == windows (groups == 1) removes the Horner step entirely (used for the circuit keys).
@@ -14,6 +20,12 @@ namespace mp {
 constexpr int MSM_CLASSES = 64;        // length classes used to order work items (longest first)
 constexpr int MSM_MAX_JOBS = 4;        // MSMs handled by one accumulate / reduce launch
 constexpr int MSM_HEAVY_SEGS = 33;     // buckets with this many slices or more are folded by a whole warp
+constexpr int PLAN_THREADS = 1024;     // threads of the per-list plan block = bucket chunks of the pair index
+constexpr int BA_BLK = 128;            // threads per block of the batched-affine round kernels
+constexpr int BA_T2 = 64;              // thread totals per second-level inversion thread
+constexpr int BA_MAX_ROUNDS = 28;
+
+bool msm_use_batched_affine();         // false when MP_MSM_XYZZ=1 is set in the environment
 
 struct MsmGeom {
     int c;            // window bits (2..16)
@@ -31,6 +43,11 @@ struct MsmGeom {
     uint32_t red_s1;         // buckets per thread in reduction level 1
     uint32_t l1pg;           // level-1 chunks per group = ceil(bpg / red_s1)
     uint32_t red_d;          // level 2 works on a red_d x red_d grid of level-1 chunks (power of two, red_d^2 >= l1pg)
+    // batched-affine accumulation
+    uint32_t ent_cap;        // entry slots per list: max_entries + n_buckets (bucket starts are padded to even)
+    uint32_t p_cap;          // affine point slots per list = ent_cap / 2 (bucket k owns slots from start[k] / 2)
+    uint32_t plan_per;       // buckets per plan chunk = ceil(n_buckets / PLAN_THREADS)
+    int ba_rounds;           // tree levels needed for the fullest possible bucket
 };
 // batch_hint: expected number of independent scalar vectors per launch (sizes the reduction chunks)
 MsmGeom msm_geom(int c, int groups, uint32_t n_scalars, uint32_t table_stride, size_t batch_hint);
@@ -46,6 +63,7 @@ struct MsmSortWs {
     uint32_t* entries = nullptr;    // [batch][max_entries] sorted (sign << 31 | table index)
     uint32_t* heavy = nullptr;      // [batch][max_heavy]   buckets split into >= MSM_HEAVY_SEGS slices
     uint32_t* n_heavy = nullptr;    // [batch]
+    uint32_t* q = nullptr;          // [batch][ba_rounds+1][PLAN_THREADS+1] pairs of round r before chunk (batched affine)
     size_t bytes(const MsmGeom& g, size_t batch) const;
 };
 int msm_sort_ws_alloc(MsmSortWs& ws, const MsmGeom& g, size_t batch, DevBuf& backing);
@@ -64,9 +82,20 @@ struct MsmJob {
     void* partial;       // [batch][max_items] XYZZ<F> partial sums, indexed by slot
     void* result;        // [batch][groups] XYZZ<F> group results after reduction
     void* scratch;       // reduction scratch, msm_reduce_scratch_bytes()
+    void* pbuf;          // [batch][p_cap] Affine<F>: tree levels of the batched-affine accumulation, bucket sums at the end
 };
-int msm_accumulate_g1(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_t st);
-int msm_accumulate_g2(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_t st);
+// Scratch of one batched-affine launch (all jobs x batch of the launch share one inversion tree per round).
+struct MsmBaWs {
+    void* prefix = nullptr;    // F per pair: thread-local prefix products of the denominators
+    uint32_t* desc = nullptr;  // 3 x u32 per pair: sources and destination
+    void* tot = nullptr;       // F per thread: product of its denominators, then its inverse
+    void* pre2 = nullptr;      // F per thread: second-level prefix products
+};
+size_t msm_ba_ws_bytes(const MsmGeom* geoms, int n_jobs, size_t batch, bool g2);
+void msm_ba_ws_bind(MsmBaWs& ws, const MsmGeom* geoms, int n_jobs, size_t batch, bool g2, void* mem);
+// ba == nullptr selects the XYZZ accumulation (jobs[].partial), otherwise batched affine (jobs[].pbuf)
+int msm_accumulate_g1(const MsmJob* jobs, int n_jobs, size_t batch, const MsmBaWs* ba, cudaStream_t st);
+int msm_accumulate_g2(const MsmJob* jobs, int n_jobs, size_t batch, const MsmBaWs* ba, cudaStream_t st);
 size_t msm_reduce_scratch_bytes(const MsmGeom& g, size_t batch, bool g2);
 int msm_reduce_g1(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_t st);
 int msm_reduce_g2(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_t st);

@@ -61,6 +61,9 @@ struct mp_batch {
     DevBuf sort_a_mem, sort_b_mem, sort_l_mem, sort_h_mem;
     MsmSortWs sort_a, sort_b, sort_l, sort_h;  // A | B1+B2 | L | H each get a list without their infinity bases
     DevBuf part_a, part_b1, part_l, part_h, part_b2;
+    DevBuf pb_a, pb_b1, pb_l, pb_h, pb_b2, ba_mem_g1, ba_mem_g2;  // batched-affine point buffers and round scratch
+    MsmBaWs ba_g1, ba_g2;
+    bool use_ba = false;
     DevBuf res_g1, res_g2, red_a, red_b1, red_l, red_h, red_b2, proofs;
     MsmGeom gz{}, gh{};
     cudaEvent_t ev[PH_COUNT + 1] = {};
@@ -284,11 +287,25 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch*
     MP_TRY(msm_sort_ws_alloc(b->sort_l, b->gz, cap, b->sort_l_mem));
     MP_TRY(msm_sort_ws_alloc(b->sort_h, b->gh, cap, b->sort_h_mem));
     const size_t g1w = XYZZ<Fq>::WORDS * 4, g2w = XYZZ<Fq2>::WORDS * 4;
-    MP_TRY(b->part_a.alloc(cap * b->gz.max_items * g1w));
-    MP_TRY(b->part_b1.alloc(cap * b->gz.max_items * g1w));
-    MP_TRY(b->part_l.alloc(cap * b->gz.max_items * g1w));
-    MP_TRY(b->part_h.alloc(cap * b->gh.max_items * g1w));
-    MP_TRY(b->part_b2.alloc(cap * b->gz.max_items * g2w));
+    b->use_ba = msm_use_batched_affine();
+    if (b->use_ba) {
+        MP_TRY(b->pb_a.alloc(cap * b->gz.p_cap * MP_G1_BYTES));
+        MP_TRY(b->pb_b1.alloc(cap * b->gz.p_cap * MP_G1_BYTES));
+        MP_TRY(b->pb_l.alloc(cap * b->gz.p_cap * MP_G1_BYTES));
+        MP_TRY(b->pb_h.alloc(cap * b->gh.p_cap * MP_G1_BYTES));
+        MP_TRY(b->pb_b2.alloc(cap * b->gz.p_cap * MP_G2_BYTES));
+        const MsmGeom geoms_g1[4] = {b->gz, b->gz, b->gz, b->gh};
+        MP_TRY(b->ba_mem_g1.alloc(msm_ba_ws_bytes(geoms_g1, 4, cap, false)));
+        msm_ba_ws_bind(b->ba_g1, geoms_g1, 4, cap, false, b->ba_mem_g1.p);
+        MP_TRY(b->ba_mem_g2.alloc(msm_ba_ws_bytes(&b->gz, 1, cap, true)));
+        msm_ba_ws_bind(b->ba_g2, &b->gz, 1, cap, true, b->ba_mem_g2.p);
+    } else {
+        MP_TRY(b->part_a.alloc(cap * b->gz.max_items * g1w));
+        MP_TRY(b->part_b1.alloc(cap * b->gz.max_items * g1w));
+        MP_TRY(b->part_l.alloc(cap * b->gz.max_items * g1w));
+        MP_TRY(b->part_h.alloc(cap * b->gh.max_items * g1w));
+        MP_TRY(b->part_b2.alloc(cap * b->gz.max_items * g2w));
+    }
     MP_TRY(b->res_g1.alloc(4 * cap * g1w));
     MP_TRY(b->res_g2.alloc(cap * g2w));
     MP_TRY(b->red_a.alloc(msm_reduce_scratch_bytes(b->gz, cap, false)));
@@ -307,7 +324,7 @@ static int batch_enqueue(mp_batch* b) {
     if (cnt == 0) return MP_OK;
     MP_TRY(use_device(c->device));
     cudaStream_t st = b->st;
-    uint64_t launches = 0;
+    const uint64_t launches0 = kernel_launch_counter();
     const size_t g1w = XYZZ<Fq>::WORDS * 4;
     cudaStream_t sg2 = b->overlap ? b->st2 : st;  // stream of the G2 path
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_PREP], st));
@@ -317,18 +334,20 @@ static int batch_enqueue(mp_batch* b) {
     MP_CUDA_TRY(cudaEventRecord(b->ev_z, st));  // z' complete: the z-lists can be sorted
     char* res1 = b->res_g1.as<char>();
     MsmJob g1[4] = {
-        {b->gz, b->sort_a, c->tab_a.p, b->part_a.p, res1, b->red_a.p},
-        {b->gz, b->sort_b, c->tab_b1.p, b->part_b1.p, res1 + cnt * g1w, b->red_b1.p},
-        {b->gz, b->sort_l, c->tab_l.p, b->part_l.p, res1 + 2 * cnt * g1w, b->red_l.p},
-        {b->gh, b->sort_h, c->tab_h.p, b->part_h.p, res1 + 3 * cnt * g1w, b->red_h.p},
+        {b->gz, b->sort_a, c->tab_a.p, b->part_a.p, res1, b->red_a.p, b->pb_a.p},
+        {b->gz, b->sort_b, c->tab_b1.p, b->part_b1.p, res1 + cnt * g1w, b->red_b1.p, b->pb_b1.p},
+        {b->gz, b->sort_l, c->tab_l.p, b->part_l.p, res1 + 2 * cnt * g1w, b->red_l.p, b->pb_l.p},
+        {b->gh, b->sort_h, c->tab_h.p, b->part_h.p, res1 + 3 * cnt * g1w, b->red_h.p, b->pb_h.p},
     };
-    MsmJob g2[1] = {{b->gz, b->sort_b, c->tab_b2.p, b->part_b2.p, b->res_g2.p, b->red_b2.p}};
+    MsmJob g2[1] = {{b->gz, b->sort_b, c->tab_b2.p, b->part_b2.p, b->res_g2.p, b->red_b2.p, b->pb_b2.p}};
+    const MsmBaWs* ba1 = b->use_ba ? &b->ba_g1 : nullptr;
+    const MsmBaWs* ba2 = b->use_ba ? &b->ba_g2 : nullptr;
     auto g2_path = [&]() -> int {
         // B list -> G2 accumulate -> G2 reduce (independent of the witness map)
         MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_b, c->valid_b.as<uint32_t>(), sg2));
         MP_CUDA_TRY(cudaEventRecord(b->ev_sort_b, sg2));
         MP_CUDA_TRY(cudaEventRecord(b->ev_g2_acc0, sg2));
-        MP_TRY(msm_accumulate_g2(g2, 1, cnt, sg2));
+        MP_TRY(msm_accumulate_g2(g2, 1, cnt, ba2, sg2));
         MP_CUDA_TRY(cudaEventRecord(b->ev_g2_acc1, sg2));
         MP_TRY(msm_reduce_g2(g2, 1, cnt, sg2));
         MP_CUDA_TRY(cudaEventRecord(b->ev_g2, sg2));
@@ -339,42 +358,35 @@ static int batch_enqueue(mp_batch* b) {
         MP_TRY(g2_path());
     }
     MP_TRY(r1cs_eval(c->r1cs, b->z_mont.p, c->zlen, cnt, c->m, b->abc.p, st));
-    launches += 2;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_WITNESS_MAP], st));
     MP_TRY(witness_map_run(c->dom, b->abc.p, b->s1.p, b->s2.p, cnt, b->h_canon.p, c->m, st));
-    launches += (c->log_m > 10 ? 6 : 3) + 1;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_SORT], st));
     MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_a, c->valid_a.as<uint32_t>(), st));
     MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_l, c->valid_l.as<uint32_t>(), st));
     MP_TRY(msm_sort(b->gh, b->h_canon.as<uint32_t>(), (size_t)c->m * 8, cnt, b->sort_h, c->valid_h.as<uint32_t>(), st));
-    launches += 12;
     if (!b->overlap) {
         MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_b, c->valid_b.as<uint32_t>(), st));
     } else {
         MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_sort_b, 0));  // the B1 job of the G1 launch reads the B list
     }
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_ACC_G1], st));
-    MP_TRY(msm_accumulate_g1(g1, 4, cnt, st));
-    launches += 2;
+    MP_TRY(msm_accumulate_g1(g1, 4, cnt, ba1, st));
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_ACC_G2], st));
     if (!b->overlap) {
         MP_CUDA_TRY(cudaEventRecord(b->ev_g2_acc0, st));
-        MP_TRY(msm_accumulate_g2(g2, 1, cnt, st));
+        MP_TRY(msm_accumulate_g2(g2, 1, cnt, ba2, st));
         MP_CUDA_TRY(cudaEventRecord(b->ev_g2_acc1, st));
     }
-    launches += 2;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_REDUCE], st));
     MP_TRY(msm_reduce_g1(g1, 4, cnt, st));
     if (!b->overlap) MP_TRY(msm_reduce_g2(g2, 1, cnt, st));
     else MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_g2, 0));
-    launches += 4;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_FINISH], st));
     k_prove_finish<<<(unsigned)cnt, 96, 0, st>>>(b->res_g1.as<XYZZ<Fq>>(), b->res_g2.as<XYZZ<Fq2>>(), b->rs.as<uint32_t>(),
                                                  (uint32_t)cnt, b->proofs.as<uint8_t>());
     MP_KERNEL_CHECK();
-    launches += 1;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_COUNT], st));
-    b->launches = launches;
+    b->launches = kernel_launch_counter() - launches0;
     b->in_flight = true;
     return MP_OK;
 }

@@ -31,6 +31,11 @@ def test_field_ops(native, field):
         out = ctypes.create_string_buffer(n * limbs * 8)
         _chk(native, native.lib().mp_debug_field_op(0, field, op, native.pack_scalars(a, limbs), native.pack_scalars(b, limbs), out, n))
         assert native.unpack_scalars(out.raw, limbs) == cref.field_op(field, op, a, b if op < 3 else None), (field, op)
+    # op 6: inversion by the binary extended Euclid (used by the batched-affine MSM) == Fermat inversion of the oracle
+    a[4:8] = [2, p - 2, (p + 1) // 2, 1 << 200]
+    out = ctypes.create_string_buffer(n * limbs * 8)
+    _chk(native, native.lib().mp_debug_field_op(0, field, 6, native.pack_scalars(a, limbs), native.pack_scalars(b, limbs), out, n))
+    assert native.unpack_scalars(out.raw, limbs) == cref.field_op(field, 4, a, None), (field, "inv_gcd")
 
 
 @pytest.mark.parametrize("group", [1, 2])
@@ -104,6 +109,36 @@ def test_msm_skewed_scalars(native):
         out = ctypes.create_string_buffer(96)
         _chk(native, native.lib().mp_msm_g1(0, bases, native.pack_scalars(sc), n, out, None))
         assert out.raw == cref.msm(1, bases, sc, threads=8)
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_msm_degenerate_pairs(native, group):
+    """Equal and opposite points inside one bucket: the pairwise trees of the batched-affine accumulation meet doublings
+    (P + P, then 2P + 2P), cancellations (P + (-P)), infinities as operands, and an MSM whose value is the point at infinity."""
+    from oracle.pyref.curves import Group
+    G = Group(C, group)
+    rng = random.Random(77 + group)
+    pb = 96 * group
+    k = rng.randrange(1, C.r)
+    P = cref.fixed_base(group, [k])
+    negP = cref.fixed_base(group, [C.r - k])
+    inf = G.serialize_uncompressed(None)
+    other = cref.fixed_base(group, [rng.randrange(1, C.r) for _ in range(40)])
+    fn = native.lib().mp_msm_g1 if group == 1 else native.lib().mp_msm_g2
+    cases = []
+    s0 = rng.randrange(C.r)
+    cases.append((P * 8, [s0] * 8))                                   # 8 copies: three levels of doublings
+    cases.append((P * 5 + negP * 5, [s0] * 10))                       # cancels to infinity
+    cases.append((P + negP + P + inf + negP + P, [s0] * 6))           # mixed, result s0 * P
+    cases.append((other + P * 3 + negP * 2 + inf * 3, [rng.randrange(C.r) for _ in range(40)] + [s0] * 8))
+    cases.append((P + negP, [s0, s0]))
+    cases.append((inf * 7, [s0] * 7))
+    for bases, sc in cases:
+        n = len(sc)
+        assert len(bases) == n * pb
+        out = ctypes.create_string_buffer(pb)
+        _chk(native, fn(0, bytes(bases), native.pack_scalars(sc), n, out, None))
+        assert out.raw == cref.msm(group, bytes(bases), sc, threads=1)
 
 
 # ---- NTT ------------------------------------------------------------------------------------------------------
