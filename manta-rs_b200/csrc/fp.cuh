@@ -509,74 +509,82 @@ struct Fp {
     }
     MP_DEV Fp inv() const { return pow_const(P::pm2(), P::BITS); }  // 0 -> 0
 
-    // Inversion by the binary extended Euclid: shifts, adds and subtracts only, so it runs on the ALU pipe and leaves
-    // the multiplier pipe (the MSM bottleneck) to the other warps.  ~1.5 * 2 * BITS single-case steps.  0 -> 0.
-    // Invariants (plain integers, a = the Montgomery limbs of *this):  x1 * a == u, x2 * a == v  (mod p).
+    // Inversion without multiplications: Kaliski's "almost Montgomery inverse" (binary extended Euclid whose cofactors
+    // are only doubled, never halved mod p) runs on the ALU pipe and leaves the multiplier pipe - the MSM bottleneck - to
+    // the other warps.  Phase 1 returns x = A^-1 2^k mod p for the limbs A of *this, BITS <= k <= 2 BITS; with A = a R the
+    // Montgomery form of a^-1 is x R^2 2^-k = x 2^(2*32N - k), applied with two Montgomery products.  0 -> 0.
     MP_COLD Fp inv_gcd() const {
         if (is_zero()) return zero();
         const uint32_t* m = P::mod();
-        uint32_t u[N], v[N], x1[N], x2[N];
+        uint32_t u[N], v[N], r[N], s[N];
 #pragma unroll
-        for (int i = 0; i < N; i++) { u[i] = l[i]; v[i] = m[i]; x1[i] = 0; x2[i] = 0; }
-        x1[0] = 1;
-        auto is_one = [](const uint32_t* a) {
-            uint32_t acc = a[0] ^ 1u;
-#pragma unroll
-            for (int i = 1; i < N; i++) acc |= a[i];
-            return acc == 0;
-        };
+        for (int i = 0; i < N; i++) { u[i] = m[i]; v[i] = l[i]; r[i] = 0; s[i] = 0; }
+        s[0] = 1;
         auto shr1 = [](uint32_t* a) {
 #pragma unroll
-            for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+            for (int i = 0; i < N - 1; i++) a[i] = __funnelshift_r(a[i], a[i + 1], 1);
             a[N - 1] >>= 1;
         };
-        auto halve_mod = [&](uint32_t* x) {  // x / 2 mod p  (x < p; x + p < 2^(32N))
-            if (x[0] & 1u) {
-                add_cc(x[0], x[0], m[0]);
+        auto shl1 = [](uint32_t* a) {  // cofactors stay < 2p < 2^(32N)
 #pragma unroll
-                for (int i = 1; i < N - 1; i++) addc_cc(x[i], x[i], m[i]);
-                addc(x[N - 1], x[N - 1], m[N - 1]);
-            }
-            shr1(x);
+            for (int i = N - 1; i > 0; i--) a[i] = __funnelshift_l(a[i - 1], a[i], 1);
+            a[0] <<= 1;
         };
-        auto sub_mod = [&](uint32_t* x, const uint32_t* y) {  // x = x - y mod p
-            uint32_t borrow = sub_raw(x, x, y);
-            if (borrow) {
-                add_cc(x[0], x[0], m[0]);
+        auto add_to = [](uint32_t* a, const uint32_t* b) {
+            add_cc(a[0], a[0], b[0]);
 #pragma unroll
-                for (int i = 1; i < N - 1; i++) addc_cc(x[i], x[i], m[i]);
-                addc(x[N - 1], x[N - 1], m[N - 1]);
-            }
+            for (int i = 1; i < N - 1; i++) addc_cc(a[i], a[i], b[i]);
+            addc(a[N - 1], a[N - 1], b[N - 1]);
         };
-        for (int it = 0; it < 4 * 32 * N; it++) {  // bound for safety; terminates long before
-            if (is_one(u) || is_one(v)) break;
+        int k = 0;
+        for (; k < 2 * 32 * N; k++) {
+            uint32_t nz = 0;
+#pragma unroll
+            for (int i = 0; i < N; i++) nz |= v[i];
+            if (!nz) break;
             if (!(u[0] & 1u)) {
                 shr1(u);
-                halve_mod(x1);
+                shl1(s);
             } else if (!(v[0] & 1u)) {
                 shr1(v);
-                halve_mod(x2);
+                shl1(r);
             } else {
-                uint32_t t[N];
-                uint32_t borrow = sub_raw(t, u, v);
-                if (!borrow) {  // u >= v
+                uint32_t t1[N], t2[N];
+                uint32_t v_lt_u = sub_raw(t1, v, u);  // borrow: v < u
+                sub_raw(t2, u, v);
+                if (v_lt_u) {  // u > v: u = (u - v) / 2, r += s, s *= 2
 #pragma unroll
-                    for (int i = 0; i < N; i++) u[i] = t[i];
-                    sub_mod(x1, x2);
-                } else {
-                    sub_raw(v, v, u);
-                    sub_mod(x2, x1);
+                    for (int i = 0; i < N; i++) u[i] = t2[i];
+                    shr1(u);
+                    add_to(r, s);
+                    shl1(s);
+                } else {       // v >= u: v = (v - u) / 2, s += r, r *= 2
+#pragma unroll
+                    for (int i = 0; i < N; i++) v[i] = t1[i];
+                    shr1(v);
+                    add_to(s, r);
+                    shl1(r);
                 }
             }
         }
-        Fp r;
-        const bool pick_u = is_one(u);
+        // r < 2p: x = p - (r mod p)
+        Fp x;
 #pragma unroll
-        for (int i = 0; i < N; i++) r.l[i] = pick_u ? x1[i] : x2[i];
-        // r = (a R)^-1 as a plain integer = a^-1 R^-1; Montgomery form of a^-1 is a^-1 R = mont_mul(r, R^3)
-        Fp r2 = from_const(P::r2());
-        Fp r3 = r2.mul_cold(r2);
-        return r.mul_cold(r3);
+        for (int i = 0; i < N; i++) x.l[i] = r[i];
+        x.reduce_once();
+        x = x.neg();
+        // x * 2^e with e = 2 * 32N - k: Montgomery products with R^2 (-> x R) and with the plain integer 2^e (-> x 2^e);
+        // exponents that would not fit under p are taken out by doublings first
+        int e = 2 * 32 * N - k;
+        Fp y = x.mul_cold(from_const(P::r2()));
+        while (e > P::BITS - 1) {
+            y = y.dbl();
+            e--;
+        }
+        Fp pw = zero();
+#pragma unroll
+        for (int i = 0; i < N; i++) pw.l[i] = (i == (e >> 5)) ? (1u << (e & 31)) : 0u;
+        return y.mul_cold(pw);
     }
 
     // canonical (non-Montgomery) integer > (p-1)/2 ?   (ark's `y > -y` flag)

@@ -83,7 +83,19 @@ struct MsmJob {
     void* result;        // [batch][groups] XYZZ<F> group results after reduction
     void* scratch;       // reduction scratch, msm_reduce_scratch_bytes()
     void* pbuf;          // [batch][p_cap] Affine<F>: tree levels of the batched-affine accumulation, bucket sums at the end
+    // batched-affine bucket reduction (row / column sums of the bucket grid, see msm_geom_rc)
+    MsmGeom g_rc;        // geometry of the row/column stage
+    MsmSortWs ws_rc;     // its segment lists (cnt, start, entries, q)
+    void* pbuf_rc;       // [batch][g_rc.p_cap] Affine<F>
+    void* result_rc;     // [batch][g_rc.groups] XYZZ<F>: weighted column / row sums per window group
 };
+// Row/column stage of the reduction  sum_k (k+1) B_k  over the 2^(c-1) buckets of a window group: with k+1 = 256 hi + lo,
+//   sum = 256 * sum_hi hi * R_hi + sum_lo lo * C_lo,   R_hi / C_lo = sums of the buckets in row hi / column lo.
+// The 2 x 2^(c-1) additions of the row and column sums are pairwise trees (batched affine, same kernels as the bucket
+// accumulation); the two weighted sums over <= 256 points run through the running-sum kernels on a 2-group geometry.
+// Segment s of group g: [g*512, g*512+255) = columns lo = 1..255, [g*512+256, g*512+512) = rows hi = 1..256.
+MsmGeom msm_geom_rc(const MsmGeom& g);
+int msm_rc_plan(const MsmGeom& g, const MsmSortWs& ws, const MsmGeom& g_rc, const MsmSortWs& ws_rc, size_t batch, cudaStream_t st);
 // Scratch of one batched-affine launch (all jobs x batch of the launch share one inversion tree per round).
 struct MsmBaWs {
     void* prefix = nullptr;    // F per pair: thread-local prefix products of the denominators
@@ -97,8 +109,13 @@ void msm_ba_ws_bind(MsmBaWs& ws, const MsmGeom* geoms, int n_jobs, size_t batch,
 int msm_accumulate_g1(const MsmJob* jobs, int n_jobs, size_t batch, const MsmBaWs* ba, cudaStream_t st);
 int msm_accumulate_g2(const MsmJob* jobs, int n_jobs, size_t batch, const MsmBaWs* ba, cudaStream_t st);
 size_t msm_reduce_scratch_bytes(const MsmGeom& g, size_t batch, bool g2);
-int msm_reduce_g1(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_t st);
-int msm_reduce_g2(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_t st);
+// The reduction in two parts, so that the caller can put the latency-bound tail on another stream:
+//   heavy: throughput work (XYZZ: level-1 running sums; batched affine: row/column trees)
+//   tail : the small weighted sums (level 2 / the 2-group running sums) -> jobs[].result
+int msm_reduce_heavy_g1(const MsmJob* jobs, int n_jobs, size_t batch, const MsmBaWs* ba, cudaStream_t st);
+int msm_reduce_heavy_g2(const MsmJob* jobs, int n_jobs, size_t batch, const MsmBaWs* ba, cudaStream_t st);
+int msm_reduce_tail_g1(const MsmJob* jobs, int n_jobs, size_t batch, const MsmBaWs* ba, cudaStream_t st);
+int msm_reduce_tail_g2(const MsmJob* jobs, int n_jobs, size_t batch, const MsmBaWs* ba, cudaStream_t st);
 
 // bitmap[i] = base i is not the point at infinity (optionally OR-ed into an existing bitmap)
 int msm_validity_g1(const void* bases, uint32_t n, uint32_t* bitmap, bool accumulate, cudaStream_t st);

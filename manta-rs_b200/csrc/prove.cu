@@ -27,9 +27,11 @@ namespace mp {
 constexpr int PROVE_C = 16;  // window bits of the circuit MSMs
 constexpr int N_EXTRA = 4;   // r, s, -rs, 1
 
-enum Phase { PH_UPLOAD = 0, PH_PREP, PH_WITNESS_MAP, PH_SORT, PH_ACC_G1, PH_ACC_G2, PH_REDUCE, PH_FINISH, PH_COUNT };
-static const char* const kPhaseNames[PH_COUNT] = {"upload",           "prep+r1cs",         "witness_map(ntt)", "msm_sort",
-                                                  "msm_accumulate_g1", "msm_accumulate_g2", "msm_reduce",       "finish"};
+// Phases of a batch in stream order (CUDA-event intervals on the main stream).  The G2 MSM runs first because it needs
+// only z; "msm_g2" = B-list sort + G2 bucket accumulation + the throughput part of its reduction.
+enum Phase { PH_UPLOAD = 0, PH_PREP, PH_G2, PH_WITNESS_MAP, PH_SORT, PH_ACC_G1, PH_REDUCE, PH_FINISH, PH_COUNT };
+static const char* const kPhaseNames[PH_COUNT] = {"upload",   "prep",              "msm_g2(sort+accumulate+reduce)", "witness_map(r1cs+ntt)",
+                                                  "msm_sort", "msm_accumulate_g1", "msm_reduce_g1",                  "finish"};
 
 }  // namespace mp
 
@@ -49,13 +51,17 @@ struct mp_ctx {
     std::mutex mu;
     std::mutex single_mu;          // serialises mp_prove callers on the cached one-proof batch
     mp_batch* single = nullptr;   // lazily created capacity-1 batch behind mp_prove
+    // Batches of one context run their throughput kernels one after the other (co-running them on the same SMs costs
+    // ~5 %); only the latency-bound tail of a batch (small weighted sums, finishing kernel) overlaps with the next one.
+    cudaEvent_t last_heavy = nullptr;    // recorded by the batch enqueued last, after its last throughput kernel
+    mp_batch* last_heavy_owner = nullptr;
 };
 
 struct mp_batch {
     mp_ctx* ctx = nullptr;
     size_t capacity = 0, count = 0;
     cudaStream_t st = nullptr, st2 = nullptr;  // main stream; second stream for the G2 path
-    cudaEvent_t ev_z = nullptr, ev_sort_b = nullptr, ev_g2 = nullptr, ev_g2_acc0 = nullptr, ev_g2_acc1 = nullptr;
+    cudaEvent_t ev_g2_heavy = nullptr, ev_g2 = nullptr, ev_heavy = nullptr, ev_tail_fork = nullptr;
     bool overlap = true;
     DevBuf z_canon, z_mont, rs, abc, s1, s2, h_canon;
     DevBuf sort_a_mem, sort_b_mem, sort_l_mem, sort_h_mem;
@@ -63,6 +69,9 @@ struct mp_batch {
     DevBuf part_a, part_b1, part_l, part_h, part_b2;
     DevBuf pb_a, pb_b1, pb_l, pb_h, pb_b2, ba_mem_g1, ba_mem_g2;  // batched-affine point buffers and round scratch
     MsmBaWs ba_g1, ba_g2;
+    MsmGeom gz_rc{}, gh_rc{};                                     // row/column stage of the bucket reduction
+    DevBuf rc_a_mem, rc_b_mem, rc_l_mem, rc_h_mem, pbrc_a, pbrc_b1, pbrc_l, pbrc_h, pbrc_b2, resrc_g1, resrc_g2;
+    MsmSortWs rc_a, rc_b, rc_l, rc_h;
     bool use_ba = false;
     DevBuf res_g1, res_g2, red_a, red_b1, red_l, red_h, red_b2, proofs;
     MsmGeom gz{}, gh{};
@@ -271,7 +280,8 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch*
     MP_CUDA_TRY(cudaStreamCreateWithPriority(&b->st, cudaStreamNonBlocking, prio));
     MP_CUDA_TRY(cudaStreamCreateWithPriority(&b->st2, cudaStreamNonBlocking, prio));
     for (auto& e : b->ev) MP_CUDA_TRY(cudaEventCreate(&e));
-    for (cudaEvent_t* e : {&b->ev_z, &b->ev_sort_b, &b->ev_g2, &b->ev_g2_acc0, &b->ev_g2_acc1}) MP_CUDA_TRY(cudaEventCreate(e));
+    for (cudaEvent_t* e : {&b->ev_g2_heavy, &b->ev_g2, &b->ev_tail_fork}) MP_CUDA_TRY(cudaEventCreate(e));
+    MP_CUDA_TRY(cudaEventCreateWithFlags(&b->ev_heavy, cudaEventDisableTiming));
     const size_t m = c->m;
     MP_TRY(b->z_canon.alloc(cap * c->zlen * 32));
     MP_TRY(b->z_mont.alloc(cap * c->zlen * 32));
@@ -299,6 +309,19 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch*
         msm_ba_ws_bind(b->ba_g1, geoms_g1, 4, cap, false, b->ba_mem_g1.p);
         MP_TRY(b->ba_mem_g2.alloc(msm_ba_ws_bytes(&b->gz, 1, cap, true)));
         msm_ba_ws_bind(b->ba_g2, &b->gz, 1, cap, true, b->ba_mem_g2.p);
+        b->gz_rc = msm_geom_rc(b->gz);
+        b->gh_rc = msm_geom_rc(b->gh);
+        MP_TRY(msm_sort_ws_alloc(b->rc_a, b->gz_rc, cap, b->rc_a_mem));
+        MP_TRY(msm_sort_ws_alloc(b->rc_b, b->gz_rc, cap, b->rc_b_mem));
+        MP_TRY(msm_sort_ws_alloc(b->rc_l, b->gz_rc, cap, b->rc_l_mem));
+        MP_TRY(msm_sort_ws_alloc(b->rc_h, b->gh_rc, cap, b->rc_h_mem));
+        MP_TRY(b->pbrc_a.alloc(cap * b->gz_rc.p_cap * MP_G1_BYTES));
+        MP_TRY(b->pbrc_b1.alloc(cap * b->gz_rc.p_cap * MP_G1_BYTES));
+        MP_TRY(b->pbrc_l.alloc(cap * b->gz_rc.p_cap * MP_G1_BYTES));
+        MP_TRY(b->pbrc_h.alloc(cap * b->gh_rc.p_cap * MP_G1_BYTES));
+        MP_TRY(b->pbrc_b2.alloc(cap * b->gz_rc.p_cap * MP_G2_BYTES));
+        MP_TRY(b->resrc_g1.alloc(4 * cap * 2 * g1w));
+        MP_TRY(b->resrc_g2.alloc(cap * 2 * g2w));
     } else {
         MP_TRY(b->part_a.alloc(cap * b->gz.max_items * g1w));
         MP_TRY(b->part_b1.alloc(cap * b->gz.max_items * g1w));
@@ -318,6 +341,8 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch*
 }
 
 // Enqueues every kernel of one batch on the batch's streams; returns without synchronising.
+// Main stream: prep -> G2 MSM (B list) -> R1CS + witness map -> A/L/H lists -> G1 MSMs -> finish.  The latency-bound
+// tail of the G2 reduction runs on the second stream beside the witness map and the G1 MSMs.
 static int batch_enqueue(mp_batch* b) {
     mp_ctx* c = b->ctx;
     const size_t cnt = b->count;
@@ -325,62 +350,54 @@ static int batch_enqueue(mp_batch* b) {
     MP_TRY(use_device(c->device));
     cudaStream_t st = b->st;
     const uint64_t launches0 = kernel_launch_counter();
-    const size_t g1w = XYZZ<Fq>::WORDS * 4;
-    cudaStream_t sg2 = b->overlap ? b->st2 : st;  // stream of the G2 path
+    const size_t g1w = XYZZ<Fq>::WORDS * 4, g2w = XYZZ<Fq2>::WORDS * 4;
+    cudaStream_t st_tail = b->overlap ? b->st2 : st;  // stream of the G2 reduction tail
+    if (c->last_heavy && c->last_heavy_owner != b) MP_CUDA_TRY(cudaStreamWaitEvent(st, c->last_heavy, 0));
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_PREP], st));
     k_prove_prep<<<dim3(div_up(c->n + 1, 256), (unsigned)cnt), 256, 0, st>>>(b->z_canon.as<uint32_t>(), b->z_mont.as<uint32_t>(),
                                                                            b->rs.as<uint32_t>(), (uint32_t)c->n, c->zlen);
     MP_KERNEL_CHECK();
-    MP_CUDA_TRY(cudaEventRecord(b->ev_z, st));  // z' complete: the z-lists can be sorted
     char* res1 = b->res_g1.as<char>();
+    char* rrc1 = b->resrc_g1.as<char>();
     MsmJob g1[4] = {
-        {b->gz, b->sort_a, c->tab_a.p, b->part_a.p, res1, b->red_a.p, b->pb_a.p},
-        {b->gz, b->sort_b, c->tab_b1.p, b->part_b1.p, res1 + cnt * g1w, b->red_b1.p, b->pb_b1.p},
-        {b->gz, b->sort_l, c->tab_l.p, b->part_l.p, res1 + 2 * cnt * g1w, b->red_l.p, b->pb_l.p},
-        {b->gh, b->sort_h, c->tab_h.p, b->part_h.p, res1 + 3 * cnt * g1w, b->red_h.p, b->pb_h.p},
+        {b->gz, b->sort_a, c->tab_a.p, b->part_a.p, res1, b->red_a.p, b->pb_a.p, b->gz_rc, b->rc_a, b->pbrc_a.p, rrc1},
+        {b->gz, b->sort_b, c->tab_b1.p, b->part_b1.p, res1 + cnt * g1w, b->red_b1.p, b->pb_b1.p, b->gz_rc, b->rc_b, b->pbrc_b1.p, rrc1 + 2 * cnt * g1w},
+        {b->gz, b->sort_l, c->tab_l.p, b->part_l.p, res1 + 2 * cnt * g1w, b->red_l.p, b->pb_l.p, b->gz_rc, b->rc_l, b->pbrc_l.p, rrc1 + 4 * cnt * g1w},
+        {b->gh, b->sort_h, c->tab_h.p, b->part_h.p, res1 + 3 * cnt * g1w, b->red_h.p, b->pb_h.p, b->gh_rc, b->rc_h, b->pbrc_h.p, rrc1 + 6 * cnt * g1w},
     };
-    MsmJob g2[1] = {{b->gz, b->sort_b, c->tab_b2.p, b->part_b2.p, b->res_g2.p, b->red_b2.p, b->pb_b2.p}};
+    MsmJob g2[1] = {{b->gz, b->sort_b, c->tab_b2.p, b->part_b2.p, b->res_g2.p, b->red_b2.p, b->pb_b2.p, b->gz_rc, b->rc_b, b->pbrc_b2.p, b->resrc_g2.p}};
+    (void)g2w;
     const MsmBaWs* ba1 = b->use_ba ? &b->ba_g1 : nullptr;
     const MsmBaWs* ba2 = b->use_ba ? &b->ba_g2 : nullptr;
-    auto g2_path = [&]() -> int {
-        // B list -> G2 accumulate -> G2 reduce (independent of the witness map)
-        MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_b, c->valid_b.as<uint32_t>(), sg2));
-        MP_CUDA_TRY(cudaEventRecord(b->ev_sort_b, sg2));
-        MP_CUDA_TRY(cudaEventRecord(b->ev_g2_acc0, sg2));
-        MP_TRY(msm_accumulate_g2(g2, 1, cnt, ba2, sg2));
-        MP_CUDA_TRY(cudaEventRecord(b->ev_g2_acc1, sg2));
-        MP_TRY(msm_reduce_g2(g2, 1, cnt, sg2));
-        MP_CUDA_TRY(cudaEventRecord(b->ev_g2, sg2));
-        return MP_OK;
-    };
+    // ---- G2 MSM over the B list
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_G2], st));
+    MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_b, c->valid_b.as<uint32_t>(), st));
+    MP_TRY(msm_accumulate_g2(g2, 1, cnt, ba2, st));
+    MP_TRY(msm_reduce_heavy_g2(g2, 1, cnt, ba2, st));
     if (b->overlap) {
-        MP_CUDA_TRY(cudaStreamWaitEvent(sg2, b->ev_z, 0));
-        MP_TRY(g2_path());
+        MP_CUDA_TRY(cudaEventRecord(b->ev_g2_heavy, st));
+        MP_CUDA_TRY(cudaStreamWaitEvent(st_tail, b->ev_g2_heavy, 0));
     }
-    MP_TRY(r1cs_eval(c->r1cs, b->z_mont.p, c->zlen, cnt, c->m, b->abc.p, st));
+    MP_TRY(msm_reduce_tail_g2(g2, 1, cnt, ba2, st_tail));
+    if (b->overlap) MP_CUDA_TRY(cudaEventRecord(b->ev_g2, st_tail));
+    // ---- witness map
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_WITNESS_MAP], st));
+    MP_TRY(r1cs_eval(c->r1cs, b->z_mont.p, c->zlen, cnt, c->m, b->abc.p, st));
     MP_TRY(witness_map_run(c->dom, b->abc.p, b->s1.p, b->s2.p, cnt, b->h_canon.p, c->m, st));
+    // ---- G1 MSMs
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_SORT], st));
     MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_a, c->valid_a.as<uint32_t>(), st));
     MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_l, c->valid_l.as<uint32_t>(), st));
     MP_TRY(msm_sort(b->gh, b->h_canon.as<uint32_t>(), (size_t)c->m * 8, cnt, b->sort_h, c->valid_h.as<uint32_t>(), st));
-    if (!b->overlap) {
-        MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_b, c->valid_b.as<uint32_t>(), st));
-    } else {
-        MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_sort_b, 0));  // the B1 job of the G1 launch reads the B list
-    }
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_ACC_G1], st));
     MP_TRY(msm_accumulate_g1(g1, 4, cnt, ba1, st));
-    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_ACC_G2], st));
-    if (!b->overlap) {
-        MP_CUDA_TRY(cudaEventRecord(b->ev_g2_acc0, st));
-        MP_TRY(msm_accumulate_g2(g2, 1, cnt, ba2, st));
-        MP_CUDA_TRY(cudaEventRecord(b->ev_g2_acc1, st));
-    }
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_REDUCE], st));
-    MP_TRY(msm_reduce_g1(g1, 4, cnt, st));
-    if (!b->overlap) MP_TRY(msm_reduce_g2(g2, 1, cnt, st));
-    else MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_g2, 0));
+    MP_TRY(msm_reduce_heavy_g1(g1, 4, cnt, ba1, st));
+    MP_CUDA_TRY(cudaEventRecord(b->ev_heavy, st));  // the next batch of this context may start its kernels now
+    c->last_heavy = b->ev_heavy;
+    c->last_heavy_owner = b;
+    MP_TRY(msm_reduce_tail_g1(g1, 4, cnt, ba1, st));
+    if (b->overlap) MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_g2, 0));
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_FINISH], st));
     k_prove_finish<<<(unsigned)cnt, 96, 0, st>>>(b->res_g1.as<XYZZ<Fq>>(), b->res_g2.as<XYZZ<Fq2>>(), b->rs.as<uint32_t>(),
                                                  (uint32_t)cnt, b->proofs.as<uint8_t>());
@@ -401,8 +418,6 @@ static int batch_finalize(mp_batch* b, float* out_ms) {
     b->in_flight = false;
     float total = 0;
     for (int ph = PH_PREP; ph < PH_COUNT; ph++) MP_CUDA_TRY(cudaEventElapsedTime(&b->phase_ms[ph], b->ev[ph], b->ev[ph + 1]));
-    // the G2 accumulate always reports its own event pair (it runs beside the other phases when overlapped)
-    MP_CUDA_TRY(cudaEventElapsedTime(&b->phase_ms[PH_ACC_G2], b->ev_g2_acc0, b->ev_g2_acc1));
     MP_CUDA_TRY(cudaEventElapsedTime(&total, b->ev[PH_PREP], b->ev[PH_COUNT]));
     b->ran = true;
     if (out_ms) *out_ms = total;
@@ -502,7 +517,12 @@ void mp_batch_destroy(mp_batch* b) {
     if (b->st2) cudaStreamSynchronize(b->st2);
     for (auto& e : b->ev)
         if (e) cudaEventDestroy(e);
-    for (cudaEvent_t e : {b->ev_z, b->ev_sort_b, b->ev_g2, b->ev_g2_acc0, b->ev_g2_acc1})
+    if (b->ctx && b->ctx->last_heavy_owner == b) {
+        std::lock_guard<std::mutex> lock(b->ctx->mu);
+        b->ctx->last_heavy = nullptr;
+        b->ctx->last_heavy_owner = nullptr;
+    }
+    for (cudaEvent_t e : {b->ev_g2_heavy, b->ev_g2, b->ev_heavy, b->ev_tail_fork})
         if (e) cudaEventDestroy(e);
     if (b->st) cudaStreamDestroy(b->st);
     if (b->st2) cudaStreamDestroy(b->st2);
