@@ -513,29 +513,26 @@ struct Fp {
     // are only doubled, never halved mod p) runs on the ALU pipe and leaves the multiplier pipe - the MSM bottleneck - to
     // the other warps.  Phase 1 returns x = A^-1 2^k mod p for the limbs A of *this, BITS <= k <= 2 BITS; with A = a R the
     // Montgomery form of a^-1 is x R^2 2^-k = x 2^(2*32N - k), applied with two Montgomery products.  0 -> 0.
+    MP_DEV static void limbs_shr1(uint32_t (&a)[N]) {
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) a[i] = __funnelshift_r(a[i], a[i + 1], 1);
+        a[N - 1] >>= 1;
+    }
+    MP_DEV static void limbs_shl1(uint32_t (&a)[N]) {
+#pragma unroll
+        for (int i = N - 1; i > 0; i--) a[i] = __funnelshift_l(a[i - 1], a[i], 1);
+        a[0] <<= 1;
+    }
     MP_COLD Fp inv_gcd() const {
         if (is_zero()) return zero();
         const uint32_t* m = P::mod();
+        // u, v: the Euclid pair; r, s: cofactors (< 2p < 2^(32N)).  Everything stays in registers: no pointers, no
+        // dynamic indices.  One of four cases per step; (u, r) and (v, s) swap roles between the symmetric ones.
         uint32_t u[N], v[N], r[N], s[N];
 #pragma unroll
         for (int i = 0; i < N; i++) { u[i] = m[i]; v[i] = l[i]; r[i] = 0; s[i] = 0; }
         s[0] = 1;
-        auto shr1 = [](uint32_t* a) {
-#pragma unroll
-            for (int i = 0; i < N - 1; i++) a[i] = __funnelshift_r(a[i], a[i + 1], 1);
-            a[N - 1] >>= 1;
-        };
-        auto shl1 = [](uint32_t* a) {  // cofactors stay < 2p < 2^(32N)
-#pragma unroll
-            for (int i = N - 1; i > 0; i--) a[i] = __funnelshift_l(a[i - 1], a[i], 1);
-            a[0] <<= 1;
-        };
-        auto add_to = [](uint32_t* a, const uint32_t* b) {
-            add_cc(a[0], a[0], b[0]);
-#pragma unroll
-            for (int i = 1; i < N - 1; i++) addc_cc(a[i], a[i], b[i]);
-            addc(a[N - 1], a[N - 1], b[N - 1]);
-        };
+        // (a branch-free formulation of the four cases was measured slower: every lane then pays for all of them)
         int k = 0;
         for (; k < 2 * 32 * N; k++) {
             uint32_t nz = 0;
@@ -543,27 +540,30 @@ struct Fp {
             for (int i = 0; i < N; i++) nz |= v[i];
             if (!nz) break;
             if (!(u[0] & 1u)) {
-                shr1(u);
-                shl1(s);
+                limbs_shr1(u);
+                limbs_shl1(s);
             } else if (!(v[0] & 1u)) {
-                shr1(v);
-                shl1(r);
+                limbs_shr1(v);
+                limbs_shl1(r);
             } else {
                 uint32_t t1[N], t2[N];
                 uint32_t v_lt_u = sub_raw(t1, v, u);  // borrow: v < u
                 sub_raw(t2, u, v);
+                uint32_t sum[N];                       // r + s: the new value of whichever cofactor is not doubled
+                add_cc(sum[0], r[0], s[0]);
+#pragma unroll
+                for (int i = 1; i < N - 1; i++) addc_cc(sum[i], r[i], s[i]);
+                addc(sum[N - 1], r[N - 1], s[N - 1]);
                 if (v_lt_u) {  // u > v: u = (u - v) / 2, r += s, s *= 2
 #pragma unroll
-                    for (int i = 0; i < N; i++) u[i] = t2[i];
-                    shr1(u);
-                    add_to(r, s);
-                    shl1(s);
+                    for (int i = 0; i < N; i++) { u[i] = t2[i]; r[i] = sum[i]; }
+                    limbs_shr1(u);
+                    limbs_shl1(s);
                 } else {       // v >= u: v = (v - u) / 2, s += r, r *= 2
 #pragma unroll
-                    for (int i = 0; i < N; i++) v[i] = t1[i];
-                    shr1(v);
-                    add_to(s, r);
-                    shl1(r);
+                    for (int i = 0; i < N; i++) { v[i] = t1[i]; s[i] = sum[i]; }
+                    limbs_shr1(v);
+                    limbs_shl1(r);
                 }
             }
         }
@@ -581,7 +581,7 @@ struct Fp {
             y = y.dbl();
             e--;
         }
-        Fp pw = zero();
+        Fp pw;
 #pragma unroll
         for (int i = 0; i < N; i++) pw.l[i] = (i == (e >> 5)) ? (1u << (e & 31)) : 0u;
         return y.mul_cold(pw);
