@@ -126,6 +126,9 @@ MP_API int mp_batch_wait(mp_batch* b, float* out_device_ms);
 /* per-phase CUDA-event times of the last mp_batch_run, in ms; names via mp_phase_name(i). Returns count. */
 MP_API int mp_batch_phase_ms(const mp_batch* b, float* out_ms, int max_phases);
 MP_API const char* mp_phase_name(int i);
+/* The dominant kernel of the last mp_batch_run (round-1 k_ba_bwd<Fq>: the first tree level of the four G1 bucket
+ * accumulations): its CUDA-event time and the number of affine additions it performed (5 Fq multiplications each). */
+MP_API int mp_batch_dominant_kernel(mp_batch* b, float* out_ms, uint64_t* out_additions);
 MP_API uint64_t mp_batch_kernel_launches(const mp_batch* b); /* kernels launched by the last mp_batch_run */
 /* overlap = 1 (default): the G2 MSM runs on a second stream next to the G1 MSMs and the witness map; overlap = 0:
  * every kernel on one stream in program order, so the per-phase CUDA-event times are those of the kernels alone. */

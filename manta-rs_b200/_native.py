@@ -60,6 +60,7 @@ SYMBOLS = {
     "mp_batch_wait": (_I, [_V, _V]),
     "mp_batch_phase_ms": (_I, [_V, _V, _I]),
     "mp_phase_name": (ctypes.c_char_p, [_I]),
+    "mp_batch_dominant_kernel": (_I, [_V, _V, _V]),
     "mp_batch_kernel_launches": (ctypes.c_uint64, [_V]),
     "mp_batch_set_overlap": (_I, [_V, _I]),
     "mp_msm_g1": (_I, [_I, _V, _V, _SZ, _V, _V]),

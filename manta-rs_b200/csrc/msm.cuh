@@ -102,6 +102,8 @@ struct MsmBaWs {
     uint32_t* desc = nullptr;  // 3 x u32 per pair: sources and destination
     void* tot = nullptr;       // F per thread: product of its denominators, then its inverse
     void* pre2 = nullptr;      // F per thread: second-level prefix products
+    // optional: recorded around the round-1 k_ba_bwd launch of the bucket trees (the dominant kernel of a proof)
+    cudaEvent_t ev_bwd0 = nullptr, ev_bwd1 = nullptr;
 };
 size_t msm_ba_ws_bytes(const MsmGeom* geoms, int n_jobs, size_t batch, bool g2);
 void msm_ba_ws_bind(MsmBaWs& ws, const MsmGeom* geoms, int n_jobs, size_t batch, bool g2, void* mem);

@@ -62,6 +62,7 @@ struct mp_batch {
     size_t capacity = 0, count = 0;
     cudaStream_t st = nullptr, st2 = nullptr;  // main stream; second stream for the G2 path
     cudaEvent_t ev_g2_heavy = nullptr, ev_g2 = nullptr, ev_heavy = nullptr, ev_tail_fork = nullptr;
+    cudaEvent_t ev_dom0 = nullptr, ev_dom1 = nullptr;  // around the dominant kernel (round-1 k_ba_bwd<Fq> of the G1 bucket trees)
     bool overlap = true;
     DevBuf z_canon, z_mont, rs, abc, s1, s2, h_canon;
     DevBuf sort_a_mem, sort_b_mem, sort_l_mem, sort_h_mem;
@@ -280,7 +281,7 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch*
     MP_CUDA_TRY(cudaStreamCreateWithPriority(&b->st, cudaStreamNonBlocking, prio));
     MP_CUDA_TRY(cudaStreamCreateWithPriority(&b->st2, cudaStreamNonBlocking, prio));
     for (auto& e : b->ev) MP_CUDA_TRY(cudaEventCreate(&e));
-    for (cudaEvent_t* e : {&b->ev_g2_heavy, &b->ev_g2, &b->ev_tail_fork}) MP_CUDA_TRY(cudaEventCreate(e));
+    for (cudaEvent_t* e : {&b->ev_g2_heavy, &b->ev_g2, &b->ev_tail_fork, &b->ev_dom0, &b->ev_dom1}) MP_CUDA_TRY(cudaEventCreate(e));
     MP_CUDA_TRY(cudaEventCreateWithFlags(&b->ev_heavy, cudaEventDisableTiming));
     const size_t m = c->m;
     MP_TRY(b->z_canon.alloc(cap * c->zlen * 32));
@@ -307,6 +308,8 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch*
         const MsmGeom geoms_g1[4] = {b->gz, b->gz, b->gz, b->gh};
         MP_TRY(b->ba_mem_g1.alloc(msm_ba_ws_bytes(geoms_g1, 4, cap, false)));
         msm_ba_ws_bind(b->ba_g1, geoms_g1, 4, cap, false, b->ba_mem_g1.p);
+        b->ba_g1.ev_bwd0 = b->ev_dom0;
+        b->ba_g1.ev_bwd1 = b->ev_dom1;
         MP_TRY(b->ba_mem_g2.alloc(msm_ba_ws_bytes(&b->gz, 1, cap, true)));
         msm_ba_ws_bind(b->ba_g2, &b->gz, 1, cap, true, b->ba_mem_g2.p);
         b->gz_rc = msm_geom_rc(b->gz);
@@ -522,7 +525,7 @@ void mp_batch_destroy(mp_batch* b) {
         b->ctx->last_heavy = nullptr;
         b->ctx->last_heavy_owner = nullptr;
     }
-    for (cudaEvent_t e : {b->ev_g2_heavy, b->ev_g2, b->ev_heavy, b->ev_tail_fork})
+    for (cudaEvent_t e : {b->ev_g2_heavy, b->ev_g2, b->ev_heavy, b->ev_tail_fork, b->ev_dom0, b->ev_dom1})
         if (e) cudaEventDestroy(e);
     if (b->st) cudaStreamDestroy(b->st);
     if (b->st2) cudaStreamDestroy(b->st2);
@@ -594,6 +597,27 @@ int mp_batch_phase_ms(const mp_batch* b, float* out_ms, int max_phases) {
     int nph = max_phases < PH_COUNT ? max_phases : PH_COUNT;
     for (int i = 0; i < nph; i++) out_ms[i] = b->phase_ms[i];
     return nph;
+}
+
+int mp_batch_dominant_kernel(mp_batch* b, float* out_ms, uint64_t* out_additions) {
+    if (!b || b->in_flight || !b->ran || !b->use_ba) return MP_ERR_INVALID_ARG;
+    MP_TRY(mp::use_device(b->ctx->device));
+    if (out_ms) MP_CUDA_TRY(cudaEventElapsedTime(out_ms, b->ev_dom0, b->ev_dom1));
+    if (out_additions) {
+        // pairs of tree level 1 = last entry of row 1 of every list's q table; the B list feeds the B1 job
+        uint64_t total = 0;
+        const MsmSortWs* lists[4] = {&b->sort_a, &b->sort_b, &b->sort_l, &b->sort_h};
+        const MsmGeom* geoms[4] = {&b->gz, &b->gz, &b->gz, &b->gh};
+        std::vector<uint32_t> host(b->count);
+        for (int i = 0; i < 4; i++) {
+            const size_t row = (size_t)(geoms[i]->ba_rounds + 1) * (PLAN_THREADS + 1);
+            MP_CUDA_TRY(cudaMemcpy2D(host.data(), 4, lists[i]->q + (size_t)(PLAN_THREADS + 1) + PLAN_THREADS, row * 4, 4, b->count,
+                                     cudaMemcpyDeviceToHost));
+            for (uint32_t v : host) total += v;
+        }
+        *out_additions = total;
+    }
+    return MP_OK;
 }
 
 const char* mp_phase_name(int i) { return (i >= 0 && i < PH_COUNT) ? kPhaseNames[i] : ""; }
