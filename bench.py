@@ -35,14 +35,30 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-SHAPE = "private_transfer"
+SHAPE = "private_transfer"     # the headline workload; --shape selects the other two circuits (BASELINE configs[0], [4])
 KEY_SEED = 21
-# credited work per PrivateTransfer proof, in Fq-multiplication equivalents
-G1_PAIRS, G2_PAIRS, REF_WINDOWS, MADD_MULS = 171031, 35174, 20, 11
-CREDIT_G1_PER_PROOF = G1_PAIRS * REF_WINDOWS * MADD_MULS            # 37.63 M
-CREDIT_G2_PER_PROOF = G2_PAIRS * REF_WINDOWS * MADD_MULS * 3        # 23.21 M
-CREDIT_PER_PROOF = CREDIT_G1_PER_PROOF + CREDIT_G2_PER_PROOF        # 60.84 M
-NTT_BYTES_PER_PROOF = 7 * 2 * 32 * 65536                            # 28 MiB algorithmic
+MADD_MULS = 11
+# credited work per proof in Fq-multiplication equivalents = pairs x reference windows x 11 (x 3 in G2)
+#                  name: (label, n, p, log_m, G1 pairs, G2 pairs, reference windows)
+SHAPE_INFO = {
+    "private_transfer": ("PrivateTransfer", 35175, 27, 16, 171031, 35174, 20),
+    "to_public": ("ToPublic", 27945, 19, 15, 116581, 27944, 22),
+    "to_private": ("ToPrivate", 8253, 13, 14, 41127, 8252, 24),
+}
+
+
+def set_shape(name):
+    global SHAPE, LABEL, WORKLOAD, CREDIT_G1_PER_PROOF, CREDIT_G2_PER_PROOF, CREDIT_PER_PROOF, NTT_BYTES_PER_PROOF
+    label, n, p, log_m, g1_pairs, g2_pairs, windows = SHAPE_INFO[name]
+    SHAPE, LABEL = name, label
+    WORKLOAD = f"{name} n={n} p={p} m=2^{log_m}"
+    CREDIT_G1_PER_PROOF = g1_pairs * windows * MADD_MULS           # PrivateTransfer: 37.63 M
+    CREDIT_G2_PER_PROOF = g2_pairs * windows * MADD_MULS * 3       # 23.21 M
+    CREDIT_PER_PROOF = CREDIT_G1_PER_PROOF + CREDIT_G2_PER_PROOF   # 60.84 M
+    NTT_BYTES_PER_PROOF = 7 * 2 * 32 * (1 << log_m)                # 28 MiB algorithmic
+
+
+set_shape(SHAPE)
 
 
 # ---- multi-rank plumbing (exercised on CPU/gloo by tests/test_multiproc_gloo.py) ------------------------------
@@ -182,12 +198,12 @@ def run_reference(args):
         op.prove(zs[i], rs[i], ss[i], threads=threads)
     dt = time.perf_counter() - t0
     value = args.steps / dt
-    sample = "1 PrivateTransfer proof per step (bounded sample of the batch), all host threads"
+    sample = f"1 {LABEL} proof per step (bounded sample of the batch), all host threads"
     line = {
-        "impl": "reference", "metric": "PrivateTransfer Groth16 proofs/sec", "value": value, "unit": "proofs/s",
+        "impl": "reference", "metric": f"{LABEL} Groth16 proofs/sec", "value": value, "unit": "proofs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (Fq 381-bit / Fr 255-bit Montgomery)",
-        "data": "synthetic", "config": {"workload": "private_transfer n=35175 p=27 m=2^16, BLS12-381, 1 proof per step on host cores"},
+        "data": "synthetic", "config": {"workload": f"{WORKLOAD}, BLS12-381, 1 proof per step on host cores"},
         "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "C++ restatement of the reference's arkworks 0.3 CPU path (no Rust toolchain in this image, so the reference "
@@ -206,10 +222,13 @@ def main():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("MP_BENCH_BATCH", "128")), help="proofs per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shape", default="private_transfer", choices=sorted(SHAPE_INFO),
+                    help="circuit shape (default: the headline PrivateTransfer workload)")
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("MP_BENCH_INFLIGHT", "2")), choices=[1, 2],
                     help="batches in flight per GPU (tuning knob; default 2)")
     ap.add_argument("--no-g2-stream", action="store_true", help="run the G2 MSM on the main stream (tuning knob)")
     args = ap.parse_args()
+    set_shape(args.shape)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
@@ -417,18 +436,19 @@ def main():
         ok = (ref0 == proofs_bytes[0:192] and ref1 == proofs_bytes[192:384] and ref2 == proofs_bytes[384:576])
         parity = "bit-exact vs CPU oracle on 3 proofs of this run" if ok else "MISMATCH vs CPU oracle"
         cpu_baseline = {"value": 1.0 / dt_all, "unit": "proofs/s", "cores": threads, "kind": "port",
-                        "sample": "2 PrivateTransfer proofs of this batch with all host threads; 1 more single-threaded",
+                        "sample": f"2 {LABEL} proofs of this batch with all host threads; 1 more single-threaded",
                         "single_thread_value": 1.0 / dt_one,
                         "note": "C++ restatement of the reference's arkworks 0.3 path; the reference as shipped is single-threaded"}
 
     if rank == 0:
         line = {
-            "metric": "PrivateTransfer Groth16 proofs/sec", "value": value, "unit": "proofs/s", "n_gpus": world,
+            "metric": f"{LABEL} Groth16 proofs/sec", "value": value, "unit": "proofs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (Fq 381-bit / Fr 255-bit Montgomery, integer pipe)",
             "data": "synthetic",
-            "config": {"workload": f"private_transfer n=35175 p=27 m=2^16 BLS12-381, batch {B} proofs/GPU/step (BASELINE configs[1] shape, "
-                                   f"configs[3] batching)", "proofs_per_step": total,
+            "config": {"workload": f"{WORKLOAD} BLS12-381, batch {B} proofs/GPU/step (BASELINE configs[1] shape, "
+                                   f"configs[3] batching)" if SHAPE == "private_transfer" else f"{WORKLOAD} BLS12-381, batch {B} proofs/GPU/step",
+                       "proofs_per_step": total,
                        "l2": "inputs larger than L2: 0.5 GB of window tables + >5 GB of per-batch buckets are streamed every step"},
             "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": B * (n * 32 + 64), "d2h_bytes_per_step": B * 192,
                     "ms_per_step": 1e3 * e2e_s / args.steps},

@@ -140,6 +140,10 @@ MP_API int mp_msm_g1(int device, const uint8_t* bases /* n x 96 */, const uint64
               uint8_t out_point[MP_G1_BYTES], float* out_device_ms);
 MP_API int mp_msm_g2(int device, const uint8_t* bases /* n x 192 */, const uint64_t* scalars, size_t n,
               uint8_t out_point[MP_G2_BYTES], float* out_device_ms);
+/* Sum of n affine points (ark uncompressed in, ark uncompressed out).  Combines the per-GPU partial results of one
+ * large MSM sharded by base range (the only exchange step of the path, 96 / 192 bytes per GPU). */
+MP_API int mp_points_sum_g1(int device, const uint8_t* points /* n x 96 */, size_t n, uint8_t out_point[MP_G1_BYTES]);
+MP_API int mp_points_sum_g2(int device, const uint8_t* points /* n x 192 */, size_t n, uint8_t out_point[MP_G2_BYTES]);
 /* in-place on `data` (2^log_n canonical Fr): inverse=0 fft / 1 ifft (with 1/n); coset=1 applies the g=7 coset
  * shift (coset_fft / coset_ifft of ark-poly).  Natural order in and out. */
 MP_API int mp_ntt(int device, uint64_t* data, unsigned log_n, int inverse, int coset, float* out_device_ms);

@@ -65,6 +65,8 @@ SYMBOLS = {
     "mp_batch_set_overlap": (_I, [_V, _I]),
     "mp_msm_g1": (_I, [_I, _V, _V, _SZ, _V, _V]),
     "mp_msm_g2": (_I, [_I, _V, _V, _SZ, _V, _V]),
+    "mp_points_sum_g1": (_I, [_I, _V, _SZ, _V]),
+    "mp_points_sum_g2": (_I, [_I, _V, _SZ, _V]),
     "mp_ntt": (_I, [_I, _V, _U, _I, _I, _V]),
     "mp_witness_map": (_I, [_V, _V, _V]),
     "mp_fixed_base_g1": (_I, [_I, _V, _SZ, _V]),

@@ -141,6 +141,31 @@ def test_msm_degenerate_pairs(native, group):
         assert out.raw == cref.msm(group, bytes(bases), sc, threads=1)
 
 
+@pytest.mark.parametrize("group", [1, 2])
+def test_points_sum_and_sharded_msm(native, group):
+    """An MSM split by base range into 3 slices (the multi-GPU sharding of BASELINE configs[4], here on one device):
+    partial sums + mp_points_sum == the single MSM == the oracle."""
+    from manta_rs_b200 import sharded
+    rng = random.Random(31 + group)
+    n, pb = 700, 96 * group
+    bases = cref.fixed_base(group, [rng.randrange(1, C.r) for _ in range(n)])
+    sc = [rng.randrange(C.r) for _ in range(n)]
+    scalars = native.pack_scalars(sc)
+    parts = b""
+    for r in range(3):
+        out, _ = sharded.msm_sharded(group, bases[:], scalars, rank=0, world=1) if r == 99 else (None, None)
+        lo, hi = sharded.shard_range(n, r, 3)
+        part, _ = sharded._native_msm(group, 0)(bases[lo * pb:hi * pb], scalars[lo * 32:hi * 32], hi - lo)
+        parts += part
+    total = sharded._native_sum(group, 0)(parts, 3)
+    whole, _ = sharded.msm_sharded(group, bases, scalars, rank=0, world=1)
+    assert total == whole == cref.msm(group, bases, sc, threads=8)
+    from oracle.pyref.curves import Group
+    inf = Group(C, group).serialize_uncompressed(None)
+    assert sharded._native_sum(group, 0)(b"", 0) == inf
+    assert sharded._native_sum(group, 0)(inf + parts[:pb] + inf, 3) == parts[:pb]
+
+
 # ---- NTT ------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("log_n", [0, 1, 2, 7, 10, 11, 13, 14, 16])
 def test_ntt_vs_oracle(native, log_n):
