@@ -157,8 +157,8 @@ MP_API int mp_fixed_base_g2(int device, const uint64_t* scalars, size_t n, uint8
 
 /* ---- diagnostics (not part of the reference interface; used by the parity tests and bench) ------------------
  * Element-wise field ops on the device: field 0 = Fq (6 limbs), 1 = Fr (4 limbs); canonical in/out.
- * op: 0 add, 1 sub, 2 mul, 3 sqr(a), 4 inv(a), 5 neg(a), 6 inv(a) by the binary extended Euclid (the batched-affine MSM's
- * inversion; same values as op 4). */
+ * op: 0 add, 1 sub, 2 mul, 3 sqr(a), 4 inv(a), 5 neg(a), 6 inv(a) by the word-level binary Euclid (the batched-affine
+ * MSM's inversion), 7 inv(a) by the bit-level almost-Montgomery inverse; both give the values of op 4. */
 MP_API int mp_debug_field_op(int device, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 /* Element-wise group ops on uncompressed points: group 1 = G1, 2 = G2.
  * op: 0 add (a + b), 1 double (a), 2 scalar mul (a * k[i], k = n x 4 limbs). */

@@ -22,6 +22,7 @@ __global__ void k_field_op(int op, const uint32_t* a, const uint32_t* b, uint32_
         case 3: r = x.sqr(); break;
         case 4: r = x.inv(); break;
         case 6: r = x.inv_gcd(); break;
+        case 7: r = x.inv_kaliski(); break;
         default: r = x.neg(); break;
     }
     r = r.from_mont();
@@ -107,7 +108,7 @@ using namespace mp;
 extern "C" {
 
 int mp_debug_field_op(int device, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
-    if (!a || !out || (field != 0 && field != 1) || op < 0 || op > 6) return MP_ERR_INVALID_ARG;
+    if (!a || !out || (field != 0 && field != 1) || op < 0 || op > 7) return MP_ERR_INVALID_ARG;
     if ((op <= 2) && !b) return MP_ERR_INVALID_ARG;
     MP_TRY(use_device(device));
     if (n == 0) return MP_OK;

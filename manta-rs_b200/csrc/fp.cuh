@@ -57,6 +57,8 @@ struct FqParams {
     MP_DEV static const uint32_t* pm2() { return FQ_PM2; }
     MP_DEV static const uint32_t* half() { return FQ_HALF; }
     MP_DEV static const uint32_t* pshift() { return FQ_PSHIFT; }
+    static constexpr int INV_ITERS = FQ_INV_ITERS;
+    MP_DEV static const uint32_t* invfix() { return FQ_INVFIX; }
 };
 struct FrParams {
     static constexpr int N = 8;
@@ -68,6 +70,8 @@ struct FrParams {
     MP_DEV static const uint32_t* pm2() { return FR_PM2; }
     MP_DEV static const uint32_t* half() { return FR_HALF; }
     MP_DEV static const uint32_t* pshift() { return FR_PSHIFT; }
+    static constexpr int INV_ITERS = FR_INV_ITERS;
+    MP_DEV static const uint32_t* invfix() { return FR_INVFIX; }
 };
 
 template <class P>
@@ -513,6 +517,150 @@ struct Fp {
     // are only doubled, never halved mod p) runs on the ALU pipe and leaves the multiplier pipe - the MSM bottleneck - to
     // the other warps.  Phase 1 returns x = A^-1 2^k mod p for the limbs A of *this, BITS <= k <= 2 BITS; with A = a R the
     // Montgomery form of a^-1 is x R^2 2^-k = x 2^(2*32N - k), applied with two Montgomery products.  0 -> 0.
+    // ---- word-level binary Euclid (the inversion of the batched-affine MSM) -------------------------------------
+    // A single warp issues about one instruction per 4 cycles, so the latency of a serial algorithm is its instruction
+    // count: the bit-level loop (inv_kaliski below, ~540 steps over 12-limb numbers) costs ~0.23 ms.  This variant follows
+    // Pornin's "optimized binary GCD": 31 bit-steps at a time run on 64-bit approximations (low 31 bits + top 33 bits of
+    // a, b) while recording the 2x2 update matrix (f0 g0; f1 g1), |entries| <= 2^31; the matrix is then applied once to the
+    // full-length a, b (exact division by 2^31) and, mod p, to the cofactors u, v (one Montgomery word step, i.e. an extra
+    // factor 2^-32).  Invariants: a 2^(31 i) = u 2^(32 i) A, b 2^(31 i) = v 2^(32 i) A (mod p).  After INV_ITERS =
+    // ceil((2 bits - 1) / 31) rounds b = 1 and A^-1 = v 2^I; with A = a R the Montgomery form of a^-1 is
+    // v 2^I R^2 = mont_mul(v, 2^I R^3).  No multiplier-pipe work except ~8 N wide MACs per round.  0 -> 0.
+
+    // out = |a f + b g| / 2^31 (exact); returns true when a f + b g < 0
+    MP_DEV static bool lin_comb_shift31(uint32_t (&out)[N], const uint32_t (&a)[N], const uint32_t (&b)[N], int64_t f, int64_t g) {
+        const bool sf = f < 0, sg = g < 0;
+        const uint32_t af = (uint32_t)(sf ? -f : f), ag = (uint32_t)(sg ? -g : g);
+        uint32_t pp[N + 1], qq[N + 1], t[N + 1];
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < N; j++) { c += (uint64_t)a[j] * af; pp[j] = (uint32_t)c; c >>= 32; }
+        pp[N] = (uint32_t)c;
+        c = 0;
+#pragma unroll
+        for (int j = 0; j < N; j++) { c += (uint64_t)b[j] * ag; qq[j] = (uint32_t)c; c >>= 32; }
+        qq[N] = (uint32_t)c;
+        bool neg;
+        if (sf == sg) {
+            add_cc(t[0], pp[0], qq[0]);
+#pragma unroll
+            for (int j = 1; j < N; j++) addc_cc(t[j], pp[j], qq[j]);
+            addc(t[N], pp[N], qq[N]);
+            neg = sf;
+        } else {
+            sub_cc(t[0], pp[0], qq[0]);
+#pragma unroll
+            for (int j = 1; j <= N; j++) subc_cc(t[j], pp[j], qq[j]);
+            uint32_t borrow;
+            subc(borrow, 0, 0);
+            if (borrow) {  // two's complement negation
+                sub_cc(t[0], 0, t[0]);
+#pragma unroll
+                for (int j = 1; j < N; j++) subc_cc(t[j], 0, t[j]);
+                subc(t[N], 0, t[N]);
+            }
+            neg = borrow ? !sf : sf;
+        }
+#pragma unroll
+        for (int j = 0; j < N; j++) out[j] = __funnelshift_r(t[j], t[j + 1], 31);
+        return neg;
+    }
+    // out = (u f + v g) / 2^32 mod p, in [0, p)
+    MP_DEV static void mod_comb(uint32_t (&out)[N], const uint32_t (&u)[N], const uint32_t (&v)[N], int64_t f, int64_t g) {
+        const uint32_t* m = P::mod();
+        const bool sf = f < 0, sg = g < 0;
+        const uint32_t af = (uint32_t)(sf ? -f : f), ag = (uint32_t)(sg ? -g : g);
+        uint32_t uu[N], vv[N], t[N + 1];
+        sub_raw(uu, m, u);  // -u = p - u (p itself when u = 0: still congruent, and the bounds below hold)
+        sub_raw(vv, m, v);
+#pragma unroll
+        for (int j = 0; j < N; j++) { uu[j] = sf ? uu[j] : u[j]; vv[j] = sg ? vv[j] : v[j]; }
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            c += (uint64_t)uu[j] * af;
+            uint64_t d = (uint64_t)vv[j] * ag;
+            uint64_t lo = (c & 0xffffffffu) + (d & 0xffffffffu);
+            t[j] = (uint32_t)lo;
+            c = (c >> 32) + (d >> 32) + (lo >> 32);
+        }
+        t[N] = (uint32_t)c;  // uu af + vv ag < 2^(32N + 31)
+        const uint32_t qm = t[0] * P::M0;
+        c = 0;
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            c += (uint64_t)m[j] * qm + t[j];
+            t[j] = (uint32_t)c;
+            c >>= 32;
+        }
+        c += t[N];
+        // t[0] == 0 now; value / 2^32 = t[1..N-1], c  (< 2p)
+        Fp r;
+#pragma unroll
+        for (int j = 0; j < N - 1; j++) r.l[j] = t[j + 1];
+        r.l[N - 1] = (uint32_t)c;
+        r.reduce_once();
+#pragma unroll
+        for (int j = 0; j < N; j++) out[j] = r.l[j];
+    }
+    MP_COLD Fp inv_gcd() const {
+        if (is_zero()) return zero();
+        const uint32_t* m = P::mod();
+        uint32_t a[N], b[N], u[N], v[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) { a[i] = l[i]; b[i] = m[i]; u[i] = 0; v[i] = 0; }
+        u[0] = 1;
+        for (int it = 0; it < P::INV_ITERS; it++) {
+            // n = max(len(a), len(b), 64); 33 top bits from bit n - 33, 31 low bits
+            uint32_t tw = 1, top = a[1] | b[1];
+#pragma unroll
+            for (int j = 2; j < N; j++) {
+                const uint32_t w = a[j] | b[j];
+                if (w) { tw = j; top = w; }
+            }
+            uint32_t n = 32 * tw + 32 - __clz(top);
+            n = n < 64 ? 64 : n;
+            const uint32_t s = n - 33, w0 = s >> 5, o = s & 31;
+            uint32_t a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+                if ((uint32_t)j == w0) { a0 = a[j]; b0 = b[j]; }
+                if ((uint32_t)j == w0 + 1) { a1 = a[j]; b1 = b[j]; }
+                if ((uint32_t)j == w0 + 2) { a2 = a[j]; b2 = b[j]; }
+            }
+            uint64_t ah = (((uint64_t)a1 << 32) | a0) >> o, bh = (((uint64_t)b1 << 32) | b0) >> o;
+            if (o) { ah |= (uint64_t)a2 << (64 - o); bh |= (uint64_t)b2 << (64 - o); }
+            const uint64_t mask33 = (1ull << 33) - 1;
+            uint64_t abar = (uint64_t)(a[0] & 0x7fffffffu) | ((ah & mask33) << 31);
+            uint64_t bbar = (uint64_t)(b[0] & 0x7fffffffu) | ((bh & mask33) << 31);
+            int64_t f0 = 1, g0 = 0, f1 = 0, g1 = 1;
+#pragma unroll 1
+            for (int j = 0; j < 31; j++) {
+                const bool odd = abar & 1u;
+                const bool sw = odd && (abar < bbar);
+                const uint64_t ta = sw ? bbar : abar, tb = sw ? abar : bbar;
+                const int64_t tf0 = sw ? f1 : f0, tf1 = sw ? f0 : f1, tg0 = sw ? g1 : g0, tg1 = sw ? g0 : g1;
+                abar = (ta - (odd ? tb : 0)) >> 1;
+                bbar = tb;
+                f0 = tf0 - (odd ? tf1 : 0);
+                g0 = tg0 - (odd ? tg1 : 0);
+                f1 = tf1 << 1;
+                g1 = tg1 << 1;
+            }
+            uint32_t na[N], nb[N], nu[N], nv[N];
+            if (lin_comb_shift31(na, a, b, f0, g0)) { f0 = -f0; g0 = -g0; }
+            if (lin_comb_shift31(nb, a, b, f1, g1)) { f1 = -f1; g1 = -g1; }
+            mod_comb(nu, u, v, f0, g0);
+            mod_comb(nv, u, v, f1, g1);
+#pragma unroll
+            for (int i = 0; i < N; i++) { a[i] = na[i]; b[i] = nb[i]; u[i] = nu[i]; v[i] = nv[i]; }
+        }
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = v[i];
+        return r.mul_cold(from_const(P::invfix()));
+    }
+
     MP_DEV static void limbs_shr1(uint32_t (&a)[N]) {
 #pragma unroll
         for (int i = 0; i < N - 1; i++) a[i] = __funnelshift_r(a[i], a[i + 1], 1);
@@ -523,7 +671,7 @@ struct Fp {
         for (int i = N - 1; i > 0; i--) a[i] = __funnelshift_l(a[i - 1], a[i], 1);
         a[0] <<= 1;
     }
-    MP_COLD Fp inv_gcd() const {
+    MP_COLD Fp inv_kaliski() const {
         if (is_zero()) return zero();
         const uint32_t* m = P::mod();
         // u, v: the Euclid pair; r, s: cofactors (< 2p < 2^(32N)).  Everything stays in registers: no pointers, no

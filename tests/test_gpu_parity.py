@@ -33,9 +33,12 @@ def test_field_ops(native, field):
         assert native.unpack_scalars(out.raw, limbs) == cref.field_op(field, op, a, b if op < 3 else None), (field, op)
     # op 6: inversion by the binary extended Euclid (used by the batched-affine MSM) == Fermat inversion of the oracle
     a[4:8] = [2, p - 2, (p + 1) // 2, 1 << 200]
-    out = ctypes.create_string_buffer(n * limbs * 8)
-    _chk(native, native.lib().mp_debug_field_op(0, field, 6, native.pack_scalars(a, limbs), native.pack_scalars(b, limbs), out, n))
-    assert native.unpack_scalars(out.raw, limbs) == cref.field_op(field, 4, a, None), (field, "inv_gcd")
+    a[8:12] = [3, p - 3, (1 << 64) - 1, (1 << 63) + 5]
+    want = cref.field_op(field, 4, a, None)
+    for op in (6, 7):
+        out = ctypes.create_string_buffer(n * limbs * 8)
+        _chk(native, native.lib().mp_debug_field_op(0, field, op, native.pack_scalars(a, limbs), native.pack_scalars(b, limbs), out, n))
+        assert native.unpack_scalars(out.raw, limbs) == want, (field, "inv_gcd", op)
 
 
 @pytest.mark.parametrize("group", [1, 2])
@@ -153,7 +156,6 @@ def test_points_sum_and_sharded_msm(native, group):
     scalars = native.pack_scalars(sc)
     parts = b""
     for r in range(3):
-        out, _ = sharded.msm_sharded(group, bases[:], scalars, rank=0, world=1) if r == 99 else (None, None)
         lo, hi = sharded.shard_range(n, r, 3)
         part, _ = sharded._native_msm(group, 0)(bases[lo * pb:hi * pb], scalars[lo * 32:hi * 32], hi - lo)
         parts += part
