@@ -155,6 +155,13 @@ MP_API int mp_witness_map(mp_ctx* ctx, const uint64_t* z, uint64_t* out_h);
 MP_API int mp_fixed_base_g1(int device, const uint64_t* scalars, size_t n, uint8_t* out /* n x 96 */);
 MP_API int mp_fixed_base_g2(int device, const uint64_t* scalars, size_t n, uint8_t* out /* n x 192 */);
 
+/* ---- witness-side Fr work -------------------------------------------------------------------
+ * Batched Poseidon permutation over BLS12-381 Fr: `Permutation::permute` of manta-pay/src/crypto/poseidon/mod.rs:385-421,
+ * 515-518 applied in place to `count` independent states of `width` elements (canonical, 4 limbs each).  round_keys:
+ * (full_rounds + partial_rounds) x width in round order; mds: width x width row-major; both canonical. */
+MP_API int mp_poseidon_permute(int device, int width, int full_rounds, int partial_rounds, const uint64_t* round_keys,
+                               const uint64_t* mds, uint64_t* states, size_t count, float* out_device_ms);
+
 /* ---- diagnostics (not part of the reference interface; used by the parity tests and bench) ------------------
  * Element-wise field ops on the device: field 0 = Fq (6 limbs), 1 = Fr (4 limbs); canonical in/out.
  * op: 0 add, 1 sub, 2 mul, 3 sqr(a), 4 inv(a), 5 neg(a), 6 inv(a) by the word-level binary Euclid (the batched-affine

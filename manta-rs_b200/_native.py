@@ -71,6 +71,7 @@ SYMBOLS = {
     "mp_witness_map": (_I, [_V, _V, _V]),
     "mp_fixed_base_g1": (_I, [_I, _V, _SZ, _V]),
     "mp_fixed_base_g2": (_I, [_I, _V, _SZ, _V]),
+    "mp_poseidon_permute": (_I, [_I, _I, _I, _I, _V, _V, _V, _SZ, _V]),
     "mp_debug_field_op": (_I, [_I, _I, _I, _V, _V, _V, _SZ]),
     "mp_debug_group_op": (_I, [_I, _I, _I, _V, _V, _V, _V, _SZ]),
     "mp_debug_int_pipe_rate": (_I, [_I, _V, _V]),

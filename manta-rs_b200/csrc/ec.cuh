@@ -216,7 +216,7 @@ struct XYZZ {
     // x = X/ZZ, y = Y/ZZZ with one inversion: i = (ZZ*ZZZ)^-1, 1/ZZ = i*ZZZ, 1/ZZZ = i*ZZ
     MP_COLD Affine<F> to_affine() const {
         if (is_inf()) return Affine<F>::inf();
-        F i = (ZZ * ZZZ).inv();
+        F i = (ZZ * ZZZ).inv_gcd();  // word-level binary Euclid: ~4x shorter than the Fermat ladder, off the multiplier pipe
         return {X * (i * ZZZ), Y * (i * ZZ)};
     }
 };

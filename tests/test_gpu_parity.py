@@ -168,6 +168,50 @@ def test_points_sum_and_sharded_msm(native, group):
     assert sharded._native_sum(group, 0)(inf + parts[:pb] + inf, 3) == parts[:pb]
 
 
+# ---- Poseidon (witness-side Fr work) ----------------------------------------------------------------------------
+def _poseidon_ref(state, rc, mds, width, rf_half, rp, r):
+    k = 0
+    for rnd in range(2 * rf_half + rp):
+        state = [(x + c) % r for x, c in zip(state, rc[k:k + width])]
+        k += width
+        full = not (rf_half <= rnd < rf_half + rp)
+        state = [pow(x, 5, r) if (full or j == 0) else x for j, x in enumerate(state)]
+        state = [sum(mds[width * i + j] * state[j] for j in range(width)) % r for i in range(width)]
+    return state
+
+
+def test_poseidon_reference_kat_and_batch(native):
+    """The reference's own known-answer vector (permutation_hardcoded_test/width3, hash.rs:248-258) through the CUDA kernel,
+    then a seeded batch (widths 3 and 5, the arities manta-pay uses) against plain Python modular arithmetic."""
+    gold = json.load(open(os.path.join(GOLD, "poseidon_bls381_width3.json")))
+    rc = [int(x, 16) for x in gold["round_constants"]]
+    mds = [int(x, 16) for x in gold["mds"]]
+    lib = native.lib()
+    st = ctypes.create_string_buffer(native.pack_scalars(gold["input"]), 3 * 32)
+    _chk(native, lib.mp_poseidon_permute(0, 3, gold["full_rounds"], gold["partial_rounds"], native.pack_scalars(rc), native.pack_scalars(mds),
+                                         st, 1, None))
+    assert [str(x) for x in native.unpack_scalars(st.raw)] == gold["expected"]
+    rng = random.Random(8)
+    for width, rf, rp, count in ((3, 8, 55, 1000), (5, 8, 56, 300), (2, 8, 3, 5)):
+        rcs = [rng.randrange(C.r) for _ in range((rf + rp) * width)] if width != 3 else rc
+        m = [rng.randrange(C.r) for _ in range(width * width)] if width != 3 else mds
+        states = [[rng.randrange(C.r) for _ in range(width)] for _ in range(count)]
+        states[0] = [0] * width
+        states[1] = [C.r - 1] * width
+        buf = ctypes.create_string_buffer(native.pack_scalars([x for s in states for x in s]), count * width * 32)
+        ms = ctypes.c_float()
+        _chk(native, lib.mp_poseidon_permute(0, width, rf, rp, native.pack_scalars(rcs), native.pack_scalars(m), buf, count, ctypes.byref(ms)))
+        got = native.unpack_scalars(buf.raw)
+        for i in (0, 1, 2, count // 2, count - 1):
+            assert got[i * width:(i + 1) * width] == _poseidon_ref(states[i], rcs, m, width, rf // 2, rp, C.r), (width, i)
+    # host mirror of the reference's Hasher: hash(inputs) = permute(domain_tag | inputs)[0]
+    from manta_rs_b200 import poseidon
+    h = poseidon.Hasher(poseidon.Permutation(3, 8, 55, rc, mds), domain_tag=3)
+    assert str(h.hash([1, 2])) == gold["expected"][0]
+    ins = [[rng.randrange(C.r), rng.randrange(C.r)] for _ in range(50)]
+    assert h.hash_many(ins) == [_poseidon_ref([3] + x, rc, mds, 3, 4, 55, C.r)[0] for x in ins]
+
+
 # ---- NTT ------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("log_n", [0, 1, 2, 7, 10, 11, 13, 14, 16])
 def test_ntt_vs_oracle(native, log_n):

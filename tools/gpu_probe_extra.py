@@ -29,6 +29,17 @@ if "--latency" in sys.argv:
                                   "phases": {lib.mp_phase_name(i).decode(): round(buf[i], 3) for i in range(8)}}
         print(shape, out["latency_" + shape], flush=True)
         lib.mp_batch_destroy(batch); ctx.close()
+if "--poseidon" in sys.argv:
+    from manta_rs_b200 import poseidon
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "poseidon_bls381_width3.json")))
+    perm = poseidon.Permutation(3, 8, 55, [int(x, 16) for x in gold["round_constants"]], [int(x, 16) for x in gold["mds"]])
+    rr = random.Random(3)
+    n = 1 << 18
+    states = [[rr.randrange(wl.FR_BLS12_381) for _ in range(3)] for _ in range(n)]
+    perm.permute_many(states[:1024])
+    perm.permute_many(states)
+    out["poseidon_width3"] = {"count": n, "device_ms": perm.last_device_ms, "Mperm_per_s": n / perm.last_device_ms / 1e3}
+    print("poseidon width 3:", out["poseidon_width3"], flush=True)
 if "--sweep" in sys.argv:
     from oracle import cref
     rng = random.Random(1)
