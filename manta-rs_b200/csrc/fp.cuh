@@ -483,7 +483,68 @@ struct Fp {
     // Karatsuba's 36 saved MACs cost more than they save, and its 16 extra registers drop a resident block.
     MP_DEV Fp operator*(const Fp& o) const { return mul_cios(o); }
 #endif
+#ifdef MP_NO_FAST_SQR
     MP_DEV Fp sqr() const { return *this * *this; }
+#else
+    // Squaring: the N (N - 1) / 2 cross products once (same even/odd split accumulators as mul_half), doubled, plus the N
+    // diagonal squares, then one Montgomery reduction: N (N + 1) / 2 + N^2 wide MACs instead of 2 N^2 (N = 12: 222 vs 288).
+    MP_DEV static void sqr_wide(uint32_t* t, const uint32_t* a) {
+        uint32_t E[2 * N + 2], O[2 * N + 2];  // E[p], E[p+1]: a product at even position p; O[p-1], O[p]: at odd position p
+#pragma unroll
+        for (int k = 0; k < 2 * N + 2; k++) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) {
+            // j = i + 1, i + 3, ...: positions i + j of parity (2 i + 1) -> odd
+            {
+                const int p0 = 2 * i + 1;
+                mad_wide_cc(O[p0 - 1], O[p0], a[i + 1], a[i]);
+                int last = p0;
+#pragma unroll
+                for (int j = i + 3; j < N; j += 2) {
+                    madc_wide_cc(O[i + j - 1], O[i + j], a[j], a[i]);
+                    last = i + j;
+                }
+                addc(O[last + 1], O[last + 1], 0);
+            }
+            // j = i + 2, i + 4, ...: positions of parity (2 i) -> even
+            if (i + 2 < N) {
+                const int p0 = 2 * i + 2;
+                mad_wide_cc(E[p0], E[p0 + 1], a[i + 2], a[i]);
+                int last = p0;
+#pragma unroll
+                for (int j = i + 4; j < N; j += 2) {
+                    madc_wide_cc(E[i + j], E[i + j + 1], a[j], a[i]);
+                    last = i + j;
+                }
+                addc(E[last + 2], E[last + 2], 0);
+            }
+        }
+        // cross = E + (O << 32), over 2N limbs
+        uint32_t c[2 * N];
+        c[0] = E[0];
+        add_cc(c[1], E[1], O[0]);
+#pragma unroll
+        for (int k = 2; k < 2 * N - 1; k++) addc_cc(c[k], E[k], O[k - 1]);
+        addc(c[2 * N - 1], E[2 * N - 1], O[2 * N - 2]);
+        // t = 2 * cross + sum a_i^2 2^(64 i)
+        uint32_t dlo, dhi;
+        mul_wide(dlo, dhi, a[0], a[0]);
+        t[0] = dlo;                                   // bit 0 of 2 * cross is 0 and c[0] == 0
+        add_cc(t[1], dhi, c[1] << 1);
+#pragma unroll
+        for (int i = 1; i < N; i++) {
+            mul_wide(dlo, dhi, a[i], a[i]);
+            addc_cc(t[2 * i], dlo, __funnelshift_l(c[2 * i - 1], c[2 * i], 1));
+            if (i < N - 1) addc_cc(t[2 * i + 1], dhi, __funnelshift_l(c[2 * i], c[2 * i + 1], 1));
+            else addc(t[2 * i + 1], dhi, __funnelshift_l(c[2 * i], c[2 * i + 1], 1));
+        }
+    }
+    MP_DEV Fp sqr() const {
+        uint32_t t[2 * N];
+        sqr_wide(t, l);
+        return redc(t);
+    }
+#endif
 
     // ---- conversions ------------------------------------------------------------------------------
     MP_COLD Fp mul_cold(const Fp& o) const { return *this * o; }

@@ -15,6 +15,7 @@
 // the MSMs (z_0 = 1 already selects query[0]).  A, B1, B2 and L then share ONE sorted digit list; H has its own.
 // All tables hold the 16 window multiples 2^(16 t) P, so each MSM is a single 2^15-bucket problem with no Horner
 // step.  Only s*g_a + r*g1_b remains as two 255-bit scalar multiplications in the finishing kernel.
+#include <cstdlib>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -631,13 +632,30 @@ int mp_batch_set_overlap(mp_batch* b, int overlap) {
 }
 
 int mp_prove_batch(mp_ctx* ctx, size_t count, const uint64_t* z, const uint64_t* r, const uint64_t* s, uint8_t* out_proofs) {
-    if (!ctx) return MP_ERR_INVALID_ARG;
+    if (!ctx || (count && (!z || !r || !s || !out_proofs))) return MP_ERR_INVALID_ARG;
     if (count == 0) return MP_OK;
+    // One batch object of at most 128 proofs (~0.4 GB of device buffers per proof) is reused over chunks of the request;
+    // when the device is short of memory the chunk is halved until the buffers fit.
+    size_t chunk = 128;
+    if (const char* e = getenv("MP_PROVE_BATCH_CHUNK")) {  // test hook / memory knob
+        long v = atol(e);
+        if (v >= 1 && v <= 60000) chunk = (size_t)v;
+    }
+    if (count < chunk) chunk = count;
     mp_batch* b = nullptr;
-    MP_TRY(mp_batch_create(ctx, count, &b));
-    int rc = mp_batch_upload(b, count, z, r, s);
-    if (rc == MP_OK) rc = mp_batch_run(b, nullptr);
-    if (rc == MP_OK) rc = mp_batch_download(b, out_proofs);
+    int rc;
+    while ((rc = mp_batch_create(ctx, chunk, &b)) == MP_ERR_OOM && chunk > 1) {
+        cudaGetLastError();  // clear the sticky allocation error
+        chunk = (chunk + 1) / 2;
+    }
+    if (rc != MP_OK) return rc;
+    const size_t n = ctx->n;
+    for (size_t done = 0; done < count && rc == MP_OK; done += chunk) {
+        const size_t c = count - done < chunk ? count - done : chunk;
+        rc = mp_batch_upload(b, c, z + done * n * 4, r + done * 4, s + done * 4);
+        if (rc == MP_OK) rc = mp_batch_run(b, nullptr);
+        if (rc == MP_OK) rc = mp_batch_download(b, out_proofs + done * MP_PROOF_BYTES);
+    }
     mp_batch_destroy(b);
     return rc;
 }

@@ -168,6 +168,21 @@ def test_points_sum_and_sharded_msm(native, group):
     assert sharded._native_sum(group, 0)(inf + parts[:pb] + inf, 3) == parts[:pb]
 
 
+def test_prove_batch_is_chunked(native, monkeypatch):
+    """mp_prove_batch reuses one bounded batch object over chunks of the request (here 5 proofs in chunks of 2)."""
+    from manta_rs_b200 import groth16 as g16
+    cs = wl.make_r1cs(3, 90, dist="R")
+    pk, trap = oracle_keygen(cs, wl.sample_trapdoor(9))
+    ctx = g16.ProvingContext.decode(pk)
+    zs = [wl.make_assignment(cs, s) for s in range(5)]
+    rs, ss = [11, 12, 13, 14, 15], [21, 22, 23, 24, 25]
+    monkeypatch.setenv("MP_PROVE_BATCH_CHUNK", "2")
+    proofs = g16.Groth16.prove_many_with_randomness(ctx, [g16.R1CS.from_workload(cs, z) for z in zs], rs, ss)
+    for z, r, s, pr in zip(zs, rs, ss, proofs):
+        assert pr.to_bytes() == trapdoor_proof_bytes(cs, trap, z, r, s)
+    ctx.close()
+
+
 # ---- Poseidon (witness-side Fr work) ----------------------------------------------------------------------------
 def _poseidon_ref(state, rc, mds, width, rf_half, rp, r):
     k = 0
