@@ -28,8 +28,8 @@ __global__ void __launch_bounds__(128) k_poseidon(const uint32_t* __restrict__ r
 #pragma unroll
         for (int j = 0; j < W; j++) {
             if (j == 0 || full) {
-                Fr x2 = st[j] * st[j];
-                st[j] = x2 * x2 * st[j];
+                Fr x2 = st[j].sqr();
+                st[j] = x2.sqr() * st[j];
             }
         }
         Fr nx[W];
