@@ -62,7 +62,7 @@ struct mp_batch {
     mp_ctx* ctx = nullptr;
     size_t capacity = 0, count = 0;
     cudaStream_t st = nullptr, st2 = nullptr;  // main stream; second stream for the G2 path
-    cudaEvent_t ev_g2_heavy = nullptr, ev_g2 = nullptr, ev_heavy = nullptr, ev_tail_fork = nullptr;
+    cudaEvent_t ev_g2_heavy = nullptr, ev_g2 = nullptr, ev_heavy = nullptr, ev_tail_fork = nullptr, ev_sort_b = nullptr;
     cudaEvent_t ev_dom0 = nullptr, ev_dom1 = nullptr;  // around the dominant kernel (round-1 k_ba_bwd<Fq> of the G1 bucket trees)
     bool overlap = true;
     DevBuf z_canon, z_mont, rs, abc, s1, s2, h_canon;
@@ -72,8 +72,8 @@ struct mp_batch {
     DevBuf pb_a, pb_b1, pb_l, pb_h, pb_b2, ba_mem_g1, ba_mem_g2;  // batched-affine point buffers and round scratch
     MsmBaWs ba_g1, ba_g2;
     MsmGeom gz_rc{}, gh_rc{};                                     // row/column stage of the bucket reduction
-    DevBuf rc_a_mem, rc_b_mem, rc_l_mem, rc_h_mem, pbrc_a, pbrc_b1, pbrc_l, pbrc_h, pbrc_b2, resrc_g1, resrc_g2;
-    MsmSortWs rc_a, rc_b, rc_l, rc_h;
+    DevBuf rc_a_mem, rc_b_mem, rc_b2_mem, rc_l_mem, rc_h_mem, pbrc_a, pbrc_b1, pbrc_l, pbrc_h, pbrc_b2, resrc_g1, resrc_g2;
+    MsmSortWs rc_a, rc_b, rc_b2, rc_l, rc_h;  // B1 and B2 keep separate row/column lists: they may run on different streams
     bool use_ba = false;
     DevBuf res_g1, res_g2, red_a, red_b1, red_l, red_h, red_b2, proofs;
     MsmGeom gz{}, gh{};
@@ -282,7 +282,7 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch*
     MP_CUDA_TRY(cudaStreamCreateWithPriority(&b->st, cudaStreamNonBlocking, prio));
     MP_CUDA_TRY(cudaStreamCreateWithPriority(&b->st2, cudaStreamNonBlocking, prio));
     for (auto& e : b->ev) MP_CUDA_TRY(cudaEventCreate(&e));
-    for (cudaEvent_t* e : {&b->ev_g2_heavy, &b->ev_g2, &b->ev_tail_fork, &b->ev_dom0, &b->ev_dom1}) MP_CUDA_TRY(cudaEventCreate(e));
+    for (cudaEvent_t* e : {&b->ev_g2_heavy, &b->ev_g2, &b->ev_tail_fork, &b->ev_sort_b, &b->ev_dom0, &b->ev_dom1}) MP_CUDA_TRY(cudaEventCreate(e));
     MP_CUDA_TRY(cudaEventCreateWithFlags(&b->ev_heavy, cudaEventDisableTiming));
     const size_t m = c->m;
     MP_TRY(b->z_canon.alloc(cap * c->zlen * 32));
@@ -317,6 +317,7 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch*
         b->gh_rc = msm_geom_rc(b->gh);
         MP_TRY(msm_sort_ws_alloc(b->rc_a, b->gz_rc, cap, b->rc_a_mem));
         MP_TRY(msm_sort_ws_alloc(b->rc_b, b->gz_rc, cap, b->rc_b_mem));
+        MP_TRY(msm_sort_ws_alloc(b->rc_b2, b->gz_rc, cap, b->rc_b2_mem));
         MP_TRY(msm_sort_ws_alloc(b->rc_l, b->gz_rc, cap, b->rc_l_mem));
         MP_TRY(msm_sort_ws_alloc(b->rc_h, b->gh_rc, cap, b->rc_h_mem));
         MP_TRY(b->pbrc_a.alloc(cap * b->gz_rc.p_cap * MP_G1_BYTES));
@@ -369,16 +370,25 @@ static int batch_enqueue(mp_batch* b) {
         {b->gz, b->sort_l, c->tab_l.p, b->part_l.p, res1 + 2 * cnt * g1w, b->red_l.p, b->pb_l.p, b->gz_rc, b->rc_l, b->pbrc_l.p, rrc1 + 4 * cnt * g1w},
         {b->gh, b->sort_h, c->tab_h.p, b->part_h.p, res1 + 3 * cnt * g1w, b->red_h.p, b->pb_h.p, b->gh_rc, b->rc_h, b->pbrc_h.p, rrc1 + 6 * cnt * g1w},
     };
-    MsmJob g2[1] = {{b->gz, b->sort_b, c->tab_b2.p, b->part_b2.p, b->res_g2.p, b->red_b2.p, b->pb_b2.p, b->gz_rc, b->rc_b, b->pbrc_b2.p, b->resrc_g2.p}};
+    MsmJob g2[1] = {{b->gz, b->sort_b, c->tab_b2.p, b->part_b2.p, b->res_g2.p, b->red_b2.p, b->pb_b2.p, b->gz_rc, b->rc_b2, b->pbrc_b2.p, b->resrc_g2.p}};
     (void)g2w;
     const MsmBaWs* ba1 = b->use_ba ? &b->ba_g1 : nullptr;
     const MsmBaWs* ba2 = b->use_ba ? &b->ba_g2 : nullptr;
-    // ---- G2 MSM over the B list
+    // ---- G2 MSM over the B list.  Large batches: on the main stream (co-running throughput kernels costs ~5 %), only the
+    // latency-bound tail of its reduction on the second stream.  Small batches leave the GPU mostly idle and are bound by the
+    // per-level latencies of the trees: the whole G2 MSM then runs on the second stream beside the witness map and the G1 MSMs.
+    const bool g2_side = b->overlap && cnt <= 16;
+    cudaStream_t sg2 = g2_side ? b->st2 : st;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_G2], st));
-    MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_b, c->valid_b.as<uint32_t>(), st));
-    MP_TRY(msm_accumulate_g2(g2, 1, cnt, ba2, st));
-    MP_TRY(msm_reduce_heavy_g2(g2, 1, cnt, ba2, st));
-    if (b->overlap) {
+    if (g2_side) {
+        MP_CUDA_TRY(cudaEventRecord(b->ev_tail_fork, st));  // z' complete
+        MP_CUDA_TRY(cudaStreamWaitEvent(sg2, b->ev_tail_fork, 0));
+    }
+    MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_b, c->valid_b.as<uint32_t>(), sg2));
+    if (g2_side) MP_CUDA_TRY(cudaEventRecord(b->ev_sort_b, sg2));  // the B1 job of the G1 launch reads the B list
+    MP_TRY(msm_accumulate_g2(g2, 1, cnt, ba2, sg2));
+    MP_TRY(msm_reduce_heavy_g2(g2, 1, cnt, ba2, sg2));
+    if (b->overlap && !g2_side) {
         MP_CUDA_TRY(cudaEventRecord(b->ev_g2_heavy, st));
         MP_CUDA_TRY(cudaStreamWaitEvent(st_tail, b->ev_g2_heavy, 0));
     }
@@ -393,6 +403,7 @@ static int batch_enqueue(mp_batch* b) {
     MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_a, c->valid_a.as<uint32_t>(), st));
     MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_l, c->valid_l.as<uint32_t>(), st));
     MP_TRY(msm_sort(b->gh, b->h_canon.as<uint32_t>(), (size_t)c->m * 8, cnt, b->sort_h, c->valid_h.as<uint32_t>(), st));
+    if (g2_side) MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_sort_b, 0));
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_ACC_G1], st));
     MP_TRY(msm_accumulate_g1(g1, 4, cnt, ba1, st));
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_REDUCE], st));
@@ -526,7 +537,7 @@ void mp_batch_destroy(mp_batch* b) {
         b->ctx->last_heavy = nullptr;
         b->ctx->last_heavy_owner = nullptr;
     }
-    for (cudaEvent_t e : {b->ev_g2_heavy, b->ev_g2, b->ev_heavy, b->ev_tail_fork, b->ev_dom0, b->ev_dom1})
+    for (cudaEvent_t e : {b->ev_g2_heavy, b->ev_g2, b->ev_heavy, b->ev_tail_fork, b->ev_sort_b, b->ev_dom0, b->ev_dom1})
         if (e) cudaEventDestroy(e);
     if (b->st) cudaStreamDestroy(b->st);
     if (b->st2) cudaStreamDestroy(b->st2);
