@@ -1,0 +1,47 @@
+"""The bench.py JSON contract (keys the driver and the judge read), on the smallest circuit shape.
+
+CPU: the reference arm (`--impl reference`, the CPU oracle timed alone).  GPU: the main arm with a tiny batch."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from helpers import ROOT
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+             "dtype", "data", "config", "e2e", "cpu_baseline"}
+
+
+def _run(args, timeout):
+    env = dict(os.environ)
+    env.pop("RANK", None)
+    env.pop("WORLD_SIZE", None)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, timeout=timeout, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    d = _run(["--impl", "reference", "--shape", "to_private", "--steps", "1", "--warmup", "0"], 600)
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference"
+    assert d["unit"] == "proofs/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "to_private" in d["config"]["workload"]
+
+
+@pytest.mark.gpu
+def test_main_arm_line_small_batch():
+    d = _run(["--shape", "to_private", "--batch", "4", "--steps", "2", "--warmup", "3"], 900)
+    assert BASE_KEYS | {"gpu_launches", "clocks", "roofline"} <= set(d)
+    assert d["parity"].startswith("bit-exact"), d["parity"]
+    assert d["gpu_launches"] > 0 and d["value"] > 0 and d["e2e"]["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 4 * (8253 * 32 + 64) and d["e2e"]["d2h_bytes_per_step"] == 4 * 192
+    rf = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(rf) and 0 < rf["frac"] < 1.2
+    cb = d["cpu_baseline"]
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(cb) and cb["kind"] == "port"
