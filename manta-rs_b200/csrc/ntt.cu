@@ -34,6 +34,32 @@ struct NttArgs {
 
 MP_DEV unsigned brev_bits(unsigned p, unsigned lg) { return lg ? (__brev(p) >> (32 - lg)) : 0u; }
 
+// ---- TMA bulk copies (cp.async.bulk, global -> shared, completion on an mbarrier) -------------------------------
+// A tile of either pass is a set of contiguous global rows (8 KiB rows in pass 2, 256-byte rows in pass 1): each row
+// is one bulk copy issued by a lane of warp 0, so the copy engine - not 256 threads doing LDG + STS - stages the tile.
+MP_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+MP_DEV void mbar_init(uint64_t* bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+MP_DEV void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+MP_DEV void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+MP_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
 // In-SMEM decimation-in-frequency transform of `seqs` sequences of 2^lg points.
 // element (j, c) at s[(j * sj + c * sc) * 8]; twiddle w_np^e at tws[e * 8].  Leaves bit-reversed order.
 MP_DEV void smem_dif(uint32_t* s, const uint32_t* tws, unsigned lg, unsigned seqs, unsigned sj, unsigned sc, bool seq_fastest) {
@@ -70,12 +96,24 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(NttArgs a) {
     uint32_t* tws = smem + (size_t)NTT_TILE * 8;
     const uint32_t* in = a.in + v * a.in_stride * 8;
     for (unsigned e = threadIdx.x; e < (n1 >> 1); e += NTT_THREADS) Fr::load(a.tw + ((size_t)e << a.l2) * 8).store(tws + (size_t)e * 8);
-    for (unsigned idx = threadIdx.x; idx < n1 * C; idx += NTT_THREADS) {
-        unsigned c = idx % C, j = idx / C;
-        size_t gi = (size_t)j * n2 + c0 + c;
-        Fr x = Fr::load(in + gi * 8);
-        if (a.pre) x = x * Fr::load(a.pre + gi * 8);
-        x.store(tile + (size_t)idx * 8);
+    __shared__ __align__(8) uint64_t bar;
+    if (!a.pre) {
+        // tile[j][c] <- in[j * n2 + c0 + c]: n1 rows of C * 32 bytes, one bulk copy each
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            if (threadIdx.x == 0) mbar_arrive_expect_tx(&bar, n1 * C * 32);
+            __syncwarp();
+            for (unsigned j = threadIdx.x; j < n1; j += 32) bulk_copy_g2s(tile + (size_t)j * C * 8, in + ((size_t)j * n2 + c0) * 8, C * 32, &bar);
+        }
+        mbar_wait(&bar, 0);
+    } else {
+        for (unsigned idx = threadIdx.x; idx < n1 * C; idx += NTT_THREADS) {
+            unsigned c = idx % C, j = idx / C;
+            size_t gi = (size_t)j * n2 + c0 + c;
+            Fr x = Fr::load(in + gi * 8) * Fr::load(a.pre + gi * 8);
+            x.store(tile + (size_t)idx * 8);
+        }
     }
     __syncthreads();
     smem_dif(tile, tws, a.l1, C, C, 1, true);
@@ -103,12 +141,24 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_rows(NttArgs a) {
     uint32_t* tws = smem + (size_t)(NTT_TILE + 64) * 8;
     const uint32_t* in = a.in + v * a.in_stride * 8;
     for (unsigned e = threadIdx.x; e < (n2 >> 1); e += NTT_THREADS) Fr::load(a.tw + ((size_t)e << a.l1) * 8).store(tws + (size_t)e * 8);
-    for (unsigned idx = threadIdx.x; idx < n2 * R; idx += NTT_THREADS) {
-        unsigned j = idx & (n2 - 1), c = idx >> a.l2;
-        size_t gi = (size_t)(r0 + c) * n2 + j;
-        Fr x = Fr::load(in + gi * 8);
-        if (a.l1 == 0 && a.pre) x = x * Fr::load(a.pre + gi * 8);
-        x.store(tile + (size_t)(c * rs + j) * 8);
+    __shared__ __align__(8) uint64_t bar;
+    if (!(a.l1 == 0 && a.pre)) {
+        // tile row c (padded stride rs) <- the n2 contiguous elements of global row r0 + c: one bulk copy per row
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            if (threadIdx.x == 0) mbar_arrive_expect_tx(&bar, R * n2 * 32);
+            __syncwarp();
+            for (unsigned c = threadIdx.x; c < R; c += 32) bulk_copy_g2s(tile + (size_t)c * rs * 8, in + (size_t)(r0 + c) * n2 * 8, n2 * 32, &bar);
+        }
+        mbar_wait(&bar, 0);
+    } else {
+        for (unsigned idx = threadIdx.x; idx < n2 * R; idx += NTT_THREADS) {
+            unsigned j = idx & (n2 - 1), c = idx >> a.l2;
+            size_t gi = (size_t)(r0 + c) * n2 + j;
+            Fr x = Fr::load(in + gi * 8) * Fr::load(a.pre + gi * 8);
+            x.store(tile + (size_t)(c * rs + j) * 8);
+        }
     }
     __syncthreads();
     smem_dif(tile, tws, a.l2, R, 1, rs, false);
