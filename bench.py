@@ -449,7 +449,7 @@ def main():
             "config": {"workload": f"{WORKLOAD} BLS12-381, batch {B} proofs/GPU/step (BASELINE configs[1] shape, "
                                    f"configs[3] batching)" if SHAPE == "private_transfer" else f"{WORKLOAD} BLS12-381, batch {B} proofs/GPU/step",
                        "proofs_per_step": total,
-                       "l2": "inputs larger than L2: 0.5 GB of window tables + >5 GB of per-batch buckets are streamed every step"},
+                       "l2": "inputs larger than L2: 0.37 GB of window tables + ~40 GB of per-batch tree levels and round scratch are streamed every step"},
             "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": B * (n * 32 + 64), "d2h_bytes_per_step": B * 192,
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_ntt": roofline_ntt,
