@@ -130,7 +130,8 @@ MP_API const char* mp_phase_name(int i);
  * accumulations): its CUDA-event time and the number of affine additions it performed (5 Fq multiplications each). */
 MP_API int mp_batch_dominant_kernel(mp_batch* b, float* out_ms, uint64_t* out_additions);
 MP_API uint64_t mp_batch_kernel_launches(const mp_batch* b); /* kernels launched by the last mp_batch_run */
-/* overlap = 1 (default): the G2 MSM runs on a second stream next to the G1 MSMs and the witness map; overlap = 0:
+/* overlap = 1 (default): the latency-bound tail of the G2 reduction (for batches of <= 16 proofs the whole G2 MSM) runs on a
+ * second stream next to the witness map and the G1 MSMs; overlap = 0:
  * every kernel on one stream in program order, so the per-phase CUDA-event times are those of the kernels alone. */
 MP_API int mp_batch_set_overlap(mp_batch* b, int overlap);
 

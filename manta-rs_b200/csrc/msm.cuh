@@ -6,7 +6,7 @@
 // Bucket accumulation has two implementations:
 //   * batched affine (default): every bucket is summed by a pairwise tree, one round per tree level; all pairs of a
 //     round (every bucket, MSM and proof of the launch) are independent affine additions that share their field
-//     inversion by Montgomery's trick (thread-local prefix products -> 64-way second level -> one binary-Euclid
+//     inversion by Montgomery's trick (thread-local prefix products -> 8..64-way second level -> one word-level binary-Euclid
 //     inversion per 64 threads on the ALU pipe).  6 field multiplications per addition instead of 10.
 //   * XYZZ (MP_MSM_XYZZ=1): one thread per bucket slice, mixed additions into an extended-Jacobian accumulator.
 // Signed c-bit digits: 2^(c-1) buckets per window group.  A "table" holds `rows` precomputed multiples
@@ -22,7 +22,7 @@ constexpr int MSM_MAX_JOBS = 4;        // MSMs handled by one accumulate / reduc
 constexpr int MSM_HEAVY_SEGS = 33;     // buckets with this many slices or more are folded by a whole warp
 constexpr int PLAN_THREADS = 1024;     // threads of the per-list plan block = bucket chunks of the pair index
 constexpr int BA_BLK = 128;            // threads per block of the batched-affine round kernels
-constexpr int BA_T2 = 64;              // thread totals per second-level inversion thread
+constexpr int BA_T2_MAX = 64;          // most thread totals one second-level inversion thread takes (chosen per round)
 constexpr int BA_MAX_ROUNDS = 28;
 
 bool msm_use_batched_affine();         // false when MP_MSM_XYZZ=1 is set in the environment
