@@ -111,3 +111,24 @@ def test_no_cpu_fallback_without_device(native):
         native.check(rc)
     data = ctypes.create_string_buffer(64)
     assert native.lib().mp_ntt(0, data, 1, 0, 0, None) in (2, 3)
+
+
+def test_chacha20_block_rfc7539_vector():
+    """The ChaCha20 block function of the rng mirror against RFC 7539 section 2.3.2 (key 00..1f, block counter 1, nonce
+    00:00:00:09:00:00:00:4a:00:00:00:00): in the djb layout rand_chacha uses, state words 12..15 are counter_lo, counter_hi,
+    stream_lo, stream_hi, so the RFC's (counter, nonce) is counter = 1 | 0x09000000 << 32, stream = 0x4a000000."""
+    import struct
+    from manta_rs_b200.rng import chacha20_block, ChaCha20Rng
+    key = struct.unpack("<8I", bytes(range(32)))
+    out = chacha20_block(key, 1 | (0x09000000 << 32), 0x4A000000)
+    want = ("e4e7f110 15593bd1 1fdd0f50 c47120a3 c7f4d1c7 0368c033 9aaa2204 4e6cd4c3 "
+            "466482d2 09aa9f07 05d7c214 a2028bd9 d19c12b5 b94e16de e883d0cb 4e3c50a2")
+    assert " ".join("%08x" % w for w in out) == want
+    # word stream: block 0 then block 1 of the same key, stream 0; next_u64 = lo | hi << 32
+    rng = ChaCha20Rng(bytes(range(32)))
+    b0 = chacha20_block(key, 0, 0)
+    assert rng.next_u64() == b0[0] | b0[1] << 32
+    for _ in range(7):
+        rng.next_u64()
+    b1 = chacha20_block(key, 1, 0)
+    assert rng.next_u32() == b1[0]
