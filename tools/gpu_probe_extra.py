@@ -16,7 +16,9 @@ if "--latency" in sys.argv:
         h = ctx.native(comp.matrices)
         batch = ctypes.c_void_p()
         nat.check(lib.mp_batch_create(h, 1, ctypes.byref(batch)))
-        zb = nat.pack_scalars(z); rb = nat.pack_scalars([12345]); sb = nat.pack_scalars([67890])
+        zb = nat.pack_scalars(z)
+        rr_ = random.Random(99)   # full-width r, s: the two 255-bit scalar multiplications of the finishing kernel are part of the latency
+        rb = nat.pack_scalars([rr_.randrange(wl.FR_BLS12_381)]); sb = nat.pack_scalars([rr_.randrange(wl.FR_BLS12_381)])
         res = []
         for it in range(6):
             t0 = time.perf_counter()
