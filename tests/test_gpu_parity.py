@@ -183,6 +183,24 @@ def test_prove_batch_is_chunked(native, monkeypatch):
     ctx.close()
 
 
+def test_prove_batch_more_than_one_device_batch(native):
+    """260 proofs through mp_prove_batch: three device batches (128 + 128 + 4) with the default chunk."""
+    from manta_rs_b200 import groth16 as g16
+    cs = wl.make_r1cs(3, 200, dist="U")
+    pk, trap = oracle_keygen(cs, wl.sample_trapdoor(10))
+    ctx = g16.ProvingContext.decode(pk)
+    count = 260
+    zs = [wl.make_assignment(cs, 1000 + s) for s in range(count)]
+    rng = random.Random(6)
+    rs = [rng.randrange(C.r) for _ in range(count)]
+    ss = [rng.randrange(C.r) for _ in range(count)]
+    proofs = g16.Groth16.prove_many_with_randomness(ctx, [g16.R1CS.from_workload(cs, z) for z in zs], rs, ss)
+    assert len(proofs) == count
+    for i in (0, 1, 127, 128, 129, 255, 256, 259):
+        assert proofs[i].to_bytes() == trapdoor_proof_bytes(cs, trap, zs[i], rs[i], ss[i]), i
+    ctx.close()
+
+
 # ---- Poseidon (witness-side Fr work) ----------------------------------------------------------------------------
 def _poseidon_ref(state, rc, mds, width, rf_half, rp, r):
     k = 0
