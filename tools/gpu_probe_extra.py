@@ -72,7 +72,16 @@ if "--sweep" in sys.argv:
         ok = res.raw == cref.fixed_base(1, [tot])
         c_ref = (logn * 69 // 100) + 2
         credited = n * ((255 + c_ref - 1) // c_ref) * 11
-        out["msm_g1_2^%d" % logn] = {"device_ms": best, "ok": ok, "credited_GFqmul_per_s": credited / best / 1e6}
-        print("msm 2^%d: %.2f ms ok=%s credited %.1f GFq-mul/s (prep %.0fs)" % (logn, best, ok, credited / best / 1e6, time.time() - t0), flush=True)
+        cpu_ms = None
+        if logn <= 20 and "--sweep-cpu" in sys.argv:   # BASELINE configs[2]: the same MSM on the host cores (CPU oracle, all threads)
+            sc_int = [int.from_bytes(sc_bytes[32 * i:32 * i + 32], "little") for i in range(n)]
+            tc = time.perf_counter()
+            cpu_res = cref.msm(1, bases, sc_int, threads=cref.lib().oracle_max_threads())
+            cpu_ms = (time.perf_counter() - tc) * 1e3
+            ok = ok and cpu_res == res.raw
+        out["msm_g1_2^%d" % logn] = {"device_ms": best, "ok": ok, "credited_GFqmul_per_s": credited / best / 1e6, "cpu_oracle_ms": cpu_ms}
+        print("msm 2^%d: %.2f ms ok=%s credited %.1f GFq-mul/s%s (prep %.0fs)" % (
+            logn, best, ok, credited / best / 1e6, "" if cpu_ms is None else ", CPU oracle (all threads) %.0f ms = %.0fx" % (cpu_ms, cpu_ms / best),
+            time.time() - t0), flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "probe_extra.json"), "w"), indent=1)
