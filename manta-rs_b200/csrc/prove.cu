@@ -121,6 +121,51 @@ MP_COLD XYZZ<F> scalar_mul_affine(const Affine<F>& p, const uint32_t* k) {
     return r;
 }
 
+// k * P on G1 with the GLV endomorphism phi(x, y) = (beta x, y) = lambda P (lambda = z^2 - 1, 128 bits): k = k2 lambda + k1 by
+// plain integer division (both halves < 2^128 because lambda^2 ~ r), then one 128-step double-and-add over
+// {P, phi(P), P + phi(P)}: 128 doublings + ~96 additions instead of 255 + ~128.  The two scalar multiplications of the
+// finishing kernel are serial single-lane chains, so this is latency, not throughput.  Valid for points of the prime-order
+// subgroup (MSM results over a well-formed proving key always are); the scalar multiplication of ark-groth16 agrees there.
+MP_COLD XYZZ<Fq> scalar_mul_glv(const Affine<Fq>& p, const uint32_t* k) {
+    if (p.is_inf()) return XYZZ<Fq>::inf();
+    // long division of the 255-bit k by lambda: quotient k2, remainder k1
+    uint32_t rem[5] = {0, 0, 0, 0, 0}, k1[4], k2[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) k2[i] = 0;
+    for (int bit = 254; bit >= 0; bit--) {
+#pragma unroll
+        for (int i = 4; i > 0; i--) rem[i] = __funnelshift_l(rem[i - 1], rem[i], 1);
+        rem[0] = (rem[0] << 1) | ((k[bit >> 5] >> (bit & 31)) & 1u);
+        uint32_t t[5], borrow;
+        sub_cc(t[0], rem[0], FR_GLV_LAMBDA[0]);
+        subc_cc(t[1], rem[1], FR_GLV_LAMBDA[1]);
+        subc_cc(t[2], rem[2], FR_GLV_LAMBDA[2]);
+        subc_cc(t[3], rem[3], FR_GLV_LAMBDA[3]);
+        subc_cc(t[4], rem[4], 0);
+        subc(borrow, 0, 0);
+        if (!borrow) {
+#pragma unroll
+            for (int i = 0; i < 5; i++) rem[i] = t[i];
+            k2[bit >> 5] |= 1u << (bit & 31);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) k1[i] = rem[i];
+    Affine<Fq> q = {p.x.mul_cold(Fq::from_const(FQ_GLV_BETA)), p.y};
+    XYZZ<Fq> pq = XYZZ<Fq>::from_affine(p).add_mixed_cold(q);
+    XYZZ<Fq> r = XYZZ<Fq>::inf();
+    int bit = 127;
+    while (bit >= 0 && !(((k1[bit >> 5] | k2[bit >> 5]) >> (bit & 31)) & 1)) bit--;
+    for (; bit >= 0; bit--) {
+        r = r.dbl();
+        const uint32_t b1 = (k1[bit >> 5] >> (bit & 31)) & 1, b2 = (k2[bit >> 5] >> (bit & 31)) & 1;
+        if (b1 & b2) r = r.add(pq);
+        else if (b1) r = r.add_mixed_cold(p);
+        else if (b2) r = r.add_mixed_cold(q);
+    }
+    return r;
+}
+
 MP_DEV void write_fq_le(uint8_t* out, const Fq& canon) {
 #pragma unroll
     for (int i = 0; i < 12; i++) {
@@ -171,10 +216,10 @@ __global__ void __launch_bounds__(96) k_prove_finish(const XYZZ<Fq>* __restrict_
         if (warp == 0) {
             Affine<Fq> a = XYZZ<Fq>::load(res_g1 + b).to_affine();
             compress_g1(out, a);
-            scalar_mul_affine<Fq>(a, s).store(sh_sa);
+            scalar_mul_glv(a, s).store(sh_sa);
         } else if (warp == 1) {
             Affine<Fq> b1 = XYZZ<Fq>::load(res_g1 + (size_t)batch + b).to_affine();
-            scalar_mul_affine<Fq>(b1, r).store(sh_rb);
+            scalar_mul_glv(b1, r).store(sh_rb);
         } else {
             Affine<Fq2> b2 = XYZZ<Fq2>::load(res_g2 + b).to_affine();
             compress_g2(out + 48, b2);

@@ -100,3 +100,24 @@ def test_unsatisfied_assignment_still_deterministic():
     pk, _ = og.setup_trapdoor(C, cs.as_dict(), *wl.sample_trapdoor(2))
     op = cref.OracleProver(og.pk_to_bytes(C, pk), cs.p, cs.w, cs.a, cs.b, cs.c)
     assert op.prove(z, 5, 6) == og.proof_to_bytes(C, og.create_proof(C, pk, cs.as_dict(), z, 5, 6))
+
+
+def test_glv_constants_of_the_finishing_kernel():
+    """The endomorphism constants generated into the CUDA constants header (tools/gen_constants.py): lambda = z^2 - 1 is a
+    primitive cube root of unity mod r, and phi(x, y) = (beta x, y) equals lambda (x, y) on G1 for the beta that is emitted."""
+    from oracle.pyref.fields import BLS12_381 as C
+    from oracle.pyref.curves import Group
+    G = Group(C, 1)
+    z = -0xd201000000010000
+    lam = (z * z - 1) % C.r
+    beta = pow(pow(2, (C.q - 1) // 3, C.q), 2, C.q)
+    assert (lam * lam + lam + 1) % C.r == 0 and lam.bit_length() == 128
+    assert beta != 1 and pow(beta, 3, C.q) == 1
+    for k in (1, 5, 123456789):
+        P = G.mul(G.gen, k)
+        assert G.mul(P, lam) == (beta * P[0] % C.q, P[1])
+    # every scalar splits as k2 * lambda + k1 with both halves below 2^128
+    assert ((C.r - 1) // lam).bit_length() <= 128
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "manta-rs_b200", "csrc", "bls12_381_constants.cuh")).read()
+    mont = beta * (1 << 384) % C.q
+    assert "FQ_GLV_BETA[12] = {" + ", ".join("0x%08xu" % ((mont >> (32 * i)) & 0xFFFFFFFF) for i in range(12)) + "}" in hdr
