@@ -62,14 +62,14 @@ MP_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // In-SMEM decimation-in-frequency transform of `seqs` sequences of 2^lg points.
 // element (j, c) at s[(j * sj + c * sc) * 8]; twiddle w_np^e at tws[e * 8].  Leaves bit-reversed order.
-MP_DEV void smem_dif(uint32_t* s, const uint32_t* tws, unsigned lg, unsigned seqs, unsigned sj, unsigned sc, bool seq_fastest) {
-    const unsigned np = 1u << lg;
+MP_DEV void smem_dif(uint32_t* s, const uint32_t* tws, unsigned lg, unsigned lseq, unsigned sj, unsigned sc, bool seq_fastest) {
+    const unsigned np = 1u << lg, seqs = 1u << lseq;  // sequence counts are powers of two: no integer division in the loops
     const unsigned total = (np >> 1) * seqs;
     for (unsigned st = 0; st < lg; st++) {
         const unsigned lh = lg - 1 - st, half = 1u << lh;
         for (unsigned e = threadIdx.x; e < total; e += NTT_THREADS) {
             unsigned c, bf;
-            if (seq_fastest) { c = e % seqs; bf = e / seqs; }
+            if (seq_fastest) { c = e & (seqs - 1); bf = e >> lseq; }
             else { bf = e & ((np >> 1) - 1); c = e >> (lg - 1); }
             unsigned jj = bf & (half - 1), blk = bf >> lh;
             unsigned i0 = (blk << (lh + 1)) + jj, i1 = i0 + half;
@@ -89,7 +89,7 @@ MP_DEV void smem_dif(uint32_t* s, const uint32_t* tws, unsigned lg, unsigned seq
 __global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(NttArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const unsigned n1 = 1u << a.l1, n2 = 1u << a.l2;
-    const unsigned C = min((unsigned)NTT_TILE >> a.l1, n2);
+    const unsigned lC = min(11u - a.l1, a.l2), C = 1u << lC;  // = min(NTT_TILE >> l1, n2)
     const unsigned c0 = blockIdx.x * C;
     const size_t v = blockIdx.y;
     uint32_t* tile = smem;
@@ -109,18 +109,18 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(NttArgs a) {
         mbar_wait(&bar, 0);
     } else {
         for (unsigned idx = threadIdx.x; idx < n1 * C; idx += NTT_THREADS) {
-            unsigned c = idx % C, j = idx / C;
+            unsigned c = idx & (C - 1), j = idx >> lC;
             size_t gi = (size_t)j * n2 + c0 + c;
             Fr x = Fr::load(in + gi * 8) * Fr::load(a.pre + gi * 8);
             x.store(tile + (size_t)idx * 8);
         }
     }
     __syncthreads();
-    smem_dif(tile, tws, a.l1, C, C, 1, true);
+    smem_dif(tile, tws, a.l1, lC, C, 1, true);
     uint32_t* out = a.out + v * a.in_stride * 8;
     const unsigned nmask = (1u << a.log_n) - 1;
     for (unsigned idx = threadIdx.x; idx < n1 * C; idx += NTT_THREADS) {
-        unsigned c = idx % C, p = idx / C;
+        unsigned c = idx & (C - 1), p = idx >> lC;
         unsigned k1 = brev_bits(p, a.l1);
         Fr x = Fr::load(tile + (size_t)idx * 8);
         unsigned te = (k1 * (c0 + c)) & nmask;
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(NttArgs a) {
 __global__ void __launch_bounds__(NTT_THREADS) k_ntt_rows(NttArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const unsigned n1 = 1u << a.l1, n2 = 1u << a.l2;
-    const unsigned R = min((unsigned)NTT_TILE >> a.l2, n1);
+    const unsigned lR = min(11u - a.l2, a.l1), R = 1u << lR;  // = min(NTT_TILE >> l2, n1)
     const unsigned r0 = blockIdx.x * R;
     const size_t v = blockIdx.y;
     const unsigned rs = n2 + 1;  // padded row stride (elements)
@@ -161,12 +161,12 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_rows(NttArgs a) {
         }
     }
     __syncthreads();
-    smem_dif(tile, tws, a.l2, R, 1, rs, false);
+    smem_dif(tile, tws, a.l2, lR, 1, rs, false);
     uint32_t* out = a.out + v * a.out_stride * 8;
     Fr pc;
     if (a.post_c) pc = Fr::load(a.post_c);
     for (unsigned idx = threadIdx.x; idx < n2 * R; idx += NTT_THREADS) {
-        unsigned c = idx % R, p = idx / R;
+        unsigned c = idx & (R - 1), p = idx >> lR;
         unsigned k2 = brev_bits(p, a.l2);
         size_t k = (size_t)(r0 + c) + ((size_t)k2 << a.l1);
         Fr x = Fr::load(tile + (size_t)(c * rs + p) * 8);
