@@ -64,8 +64,44 @@ MP_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
 // element (j, c) at s[(j * sj + c * sc) * 8]; twiddle w_np^e at tws[e * 8].  Leaves bit-reversed order.
 MP_DEV void smem_dif(uint32_t* s, const uint32_t* tws, unsigned lg, unsigned lseq, unsigned sj, unsigned sc, bool seq_fastest) {
     const unsigned np = 1u << lg, seqs = 1u << lseq;  // sequence counts are powers of two: no integer division in the loops
+    // Two levels per shared-memory round trip (radix-4 step: the four elements i0, i0 + q, i0 + 2q, i0 + 3q of a block stay in
+    // registers between the levels), one plain radix-2 level at the end when lg is odd.  Same multiplications, half the
+    // LDS/STS traffic and barriers.
+    unsigned st = 0;
+    for (; st + 1 < lg; st += 2) {
+        const unsigned lh = lg - 1 - st, half = 1u << lh, quarter = half >> 1;
+        const unsigned quads = (np >> 2) * seqs;
+        for (unsigned e = threadIdx.x; e < quads; e += NTT_THREADS) {
+            unsigned c, q;
+            if (seq_fastest) { c = e & (seqs - 1); q = e >> lseq; }
+            else { q = e & ((np >> 2) - 1); c = e >> (lg - 2); }
+            const unsigned jj = q & (quarter - 1), blk = q >> (lh - 1);
+            const unsigned i0 = (blk << (lh + 1)) + jj;
+            uint32_t* p0 = s + (size_t)(i0 * sj + c * sc) * 8;
+            uint32_t* p1 = s + (size_t)((i0 + quarter) * sj + c * sc) * 8;
+            uint32_t* p2 = s + (size_t)((i0 + half) * sj + c * sc) * 8;
+            uint32_t* p3 = s + (size_t)((i0 + half + quarter) * sj + c * sc) * 8;
+            const Fr a0 = Fr::load(p0), a1 = Fr::load(p1), a2 = Fr::load(p2), a3 = Fr::load(p3);
+            // level st: (a0, a2) with w^(jj << st), (a1, a3) with w^((jj + quarter) << st)
+            Fr u0 = a0 + a2, d0 = a0 - a2, u1 = a1 + a3, d1 = a1 - a3;
+            if (jj) d0 = d0 * Fr::load(tws + (size_t)(jj << st) * 8);
+            d1 = d1 * Fr::load(tws + (size_t)((jj + quarter) << st) * 8);
+            // level st + 1: (u0, u1) and (d0, d1), both with w^(jj << (st + 1))
+            Fr o1 = u0 - u1, o3 = d0 - d1;
+            if (jj) {
+                const Fr t = Fr::load(tws + (size_t)(jj << (st + 1)) * 8);
+                o1 = o1 * t;
+                o3 = o3 * t;
+            }
+            (u0 + u1).store(p0);
+            o1.store(p1);
+            (d0 + d1).store(p2);
+            o3.store(p3);
+        }
+        __syncthreads();
+    }
     const unsigned total = (np >> 1) * seqs;
-    for (unsigned st = 0; st < lg; st++) {
+    for (; st < lg; st++) {
         const unsigned lh = lg - 1 - st, half = 1u << lh;
         for (unsigned e = threadIdx.x; e < total; e += NTT_THREADS) {
             unsigned c, bf;
@@ -86,7 +122,7 @@ MP_DEV void smem_dif(uint32_t* s, const uint32_t* tws, unsigned lg, unsigned lse
 }
 
 // pass 1 (columns): blockIdx.x = column tile, blockIdx.y = vector
-__global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(NttArgs a) {
+__global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_cols(NttArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const unsigned n1 = 1u << a.l1, n2 = 1u << a.l2;
     const unsigned lC = min(11u - a.l1, a.l2), C = 1u << lC;  // = min(NTT_TILE >> l1, n2)
@@ -130,7 +166,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(NttArgs a) {
 }
 
 // pass 2 (rows) — also the whole transform when l1 == 0
-__global__ void __launch_bounds__(NTT_THREADS) k_ntt_rows(NttArgs a) {
+__global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_rows(NttArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const unsigned n1 = 1u << a.l1, n2 = 1u << a.l2;
     const unsigned lR = min(11u - a.l2, a.l1), R = 1u << lR;  // = min(NTT_TILE >> l2, n1)
