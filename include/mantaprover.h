@@ -174,6 +174,11 @@ MP_API int mp_debug_group_op(int device, int group, int op, const uint8_t* a, co
                       uint8_t* out, size_t n);
 /* Sustained integer-pipe rate: independent IMAD.WIDE.U32 chains on every SM; returns wide-MACs per second
  * and the measured Fq Montgomery products per second of the production multiply. */
+/* Host-only: launch geometry of the batched-affine bucket trees for one list of n_scalars scalars with window c and `groups`
+ * bucket sets (0 = one per window): the pair capacity the launcher sizes round `round` for, the number of tree levels it
+ * provisions, buckets and the entry bound.  Lets the CPU tests check the capacity bound against worst-case bucket loads. */
+MP_API int mp_debug_ba_geometry(int c, int groups, uint32_t n_scalars, int round, uint32_t* out_pair_cap, int* out_rounds,
+                                uint32_t* out_buckets, uint32_t* out_max_entries);
 MP_API int mp_debug_int_pipe_rate(int device, double* out_wide_mac_per_s, double* out_fq_mul_per_s);
 
 #ifdef __cplusplus

@@ -74,6 +74,7 @@ SYMBOLS = {
     "mp_poseidon_permute": (_I, [_I, _I, _I, _I, _V, _V, _V, _SZ, _V]),
     "mp_debug_field_op": (_I, [_I, _I, _I, _V, _V, _V, _SZ]),
     "mp_debug_group_op": (_I, [_I, _I, _I, _V, _V, _V, _V, _SZ]),
+    "mp_debug_ba_geometry": (_I, [_I, _I, _U, _I, _V, _V, _V, _V]),
     "mp_debug_int_pipe_rate": (_I, [_I, _V, _V]),
 }
 

@@ -132,3 +132,54 @@ def test_chacha20_block_rfc7539_vector():
         rng.next_u64()
     b1 = chacha20_block(key, 1, 0)
     assert rng.next_u32() == b1[0]
+
+
+def test_batched_affine_pair_capacity_covers_worst_case_bucket_loads():
+    """Level r of the bucket trees adds floor(ceil(c / 2^(r-1)) / 2) pairs in a bucket with c entries.  The launcher sizes every
+    level for a capacity computed from the geometry alone (the bucket loads are only known on the device): it must cover every
+    distribution of at most max_entries entries over the buckets, and the provisioned number of levels must reach a bucket
+    that holds every entry."""
+    import ctypes
+    import random
+    from manta_rs_b200 import _native as nat
+    lib = nat.lib()
+
+    def geometry(c, groups, n, r):
+        cap, rounds, nb, me = ctypes.c_uint32(), ctypes.c_int(), ctypes.c_uint32(), ctypes.c_uint32()
+        nat.check(lib.mp_debug_ba_geometry(c, groups, n, r, ctypes.byref(cap), ctypes.byref(rounds), ctypes.byref(nb), ctypes.byref(me)))
+        return cap.value, rounds.value, nb.value, me.value
+
+    def pairs(counts, r):
+        return sum((((c + (1 << (r - 1)) - 1) >> (r - 1)) >> 1) for c in counts)
+
+    rng = random.Random(4)
+    for c, groups, n in ((16, 1, 35179), (16, 1, 65536), (13, 0, 70000), (4, 0, 9), (8, 1, 1000), (16, 1, 1)):
+        _, rounds, nb, me = geometry(c, groups, n, 1)
+        windows = 255 // c + 1
+        geff = windows if (groups <= 0 or groups > windows) else groups
+        fullest = min(me, n * -(-windows // geff))      # one entry per (scalar, table row) at most
+        assert (1 << rounds) >= fullest
+        loads = []
+        loads.append([me] + [0] * (nb - 1))                                     # everything in one bucket
+        base, extra = divmod(me, nb)
+        loads.append([base + (1 if i < extra else 0) for i in range(nb)])       # as even as possible
+        for r in range(2, 8):                                                   # buckets of 2^(r-1) + 1 entries: one pair each at level r
+            k = (1 << (r - 1)) + 1
+            full = min(nb, me // k)
+            loads.append([k] * full + [0] * (nb - full))
+        loads.append([3] * min(nb, me // 3) + [0] * (nb - min(nb, me // 3)))
+        for _ in range(3):                                                      # random skew
+            left, v = me, []
+            for _ in range(nb):
+                x = min(left, int(rng.expovariate(nb / max(me, 1)) * 2))
+                v.append(x)
+                left -= x
+            loads.append(v)
+        for counts in loads:
+            assert sum(counts) <= me and len(counts) == nb
+            for r in range(1, rounds + 1):
+                cap = geometry(c, groups, n, r)[0]
+                assert pairs(counts, r) <= cap, (c, groups, n, r, pairs(counts, r), cap)
+            assert pairs(counts, rounds + 1) == 0 or max(counts) > (1 << rounds)
+        # the fullest possible bucket is exhausted by the provisioned levels
+        assert pairs([fullest] + [0] * (nb - 1), rounds + 1) == 0 and (fullest < 2 or pairs([fullest], rounds) >= 1)
