@@ -48,6 +48,7 @@ extern "C" {
 #define MP_G1_BYTES 96     /* uncompressed */
 #define MP_G2_BYTES 192    /* uncompressed */
 #define MP_PROOF_BYTES 192 /* compressed A(48) | B(96) | C(48): `proof_as_bytes`, groth16.rs:184-195 */
+#define MP_MAX_BATCH 21845 /* proofs per batch object (3 vectors per proof ride in gridDim.y of the NTT launches) */
 
 typedef struct mp_ctx mp_ctx;
 typedef struct mp_batch mp_batch;
@@ -172,13 +173,17 @@ MP_API int mp_debug_field_op(int device, int field, int op, const uint64_t* a, c
  * op: 0 add (a + b), 1 double (a), 2 scalar mul (a * k[i], k = n x 4 limbs). */
 MP_API int mp_debug_group_op(int device, int group, int op, const uint8_t* a, const uint8_t* b, const uint64_t* k,
                       uint8_t* out, size_t n);
-/* Sustained integer-pipe rate: independent IMAD.WIDE.U32 chains on every SM; returns wide-MACs per second
- * and the measured Fq Montgomery products per second of the production multiply. */
 /* Host-only: launch geometry of the batched-affine bucket trees for one list of n_scalars scalars with window c and `groups`
  * bucket sets (0 = one per window): the pair capacity the launcher sizes round `round` for, the number of tree levels it
  * provisions, buckets and the entry bound.  Lets the CPU tests check the capacity bound against worst-case bucket loads. */
 MP_API int mp_debug_ba_geometry(int c, int groups, uint32_t n_scalars, int round, uint32_t* out_pair_cap, int* out_rounds,
                                 uint32_t* out_buckets, uint32_t* out_max_entries);
+/* Host-only: batched-affine round scratch of the prover for a circuit with n_vars variables and the given domain size:
+ * out = {pair slots, thread slots} a live batch of `count` proofs needs, then {pair slots, thread slots} a batch object of
+ * `capacity` provides.  The CPU tests sweep count <= capacity at the reference shapes (a partial batch re-plans its rounds). */
+MP_API int mp_debug_prove_ba_demand(uint32_t n_vars, uint32_t domain_size, size_t capacity, size_t count, int g2, uint64_t out[4]);
+/* Sustained integer-pipe rate: independent IMAD.WIDE.U32 chains on every SM; returns wide-MACs per second
+ * and the measured Fq Montgomery products per second of the production multiply. */
 MP_API int mp_debug_int_pipe_rate(int device, double* out_wide_mac_per_s, double* out_fq_mul_per_s);
 
 #ifdef __cplusplus

@@ -75,6 +75,7 @@ SYMBOLS = {
     "mp_debug_field_op": (_I, [_I, _I, _I, _V, _V, _V, _SZ]),
     "mp_debug_group_op": (_I, [_I, _I, _I, _V, _V, _V, _V, _SZ]),
     "mp_debug_ba_geometry": (_I, [_I, _I, _U, _I, _V, _V, _V, _V]),
+    "mp_debug_prove_ba_demand": (_I, [_U, _U, _SZ, _SZ, _I, _V]),
     "mp_debug_int_pipe_rate": (_I, [_I, _V, _V]),
 }
 

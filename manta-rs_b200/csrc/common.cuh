@@ -65,6 +65,33 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// RAII pair of timing events around a region of one stream (destroyed on every return path; never throws)
+struct EventTimer {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    EventTimer() = default;
+    EventTimer(const EventTimer&) = delete;
+    EventTimer& operator=(const EventTimer&) = delete;
+    ~EventTimer() {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+    int start(cudaStream_t st) {
+        if (!e0) MP_CUDA_TRY(cudaEventCreate(&e0));
+        if (!e1) MP_CUDA_TRY(cudaEventCreate(&e1));
+        MP_CUDA_TRY(cudaEventRecord(e0, st));
+        return MP_OK;
+    }
+    int stop(cudaStream_t st) {
+        MP_CUDA_TRY(cudaEventRecord(e1, st));
+        return MP_OK;
+    }
+    int elapsed_ms(float* ms) {  // waits for the stop event
+        MP_CUDA_TRY(cudaEventSynchronize(e1));
+        MP_CUDA_TRY(cudaEventElapsedTime(ms, e0, e1));
+        return MP_OK;
+    }
+};
+
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 // ---- ark-serialize <-> device layout ----------------------------------------------------------------

@@ -172,20 +172,17 @@ int mp_debug_int_pipe_rate(int device, double* out_wide_mac_per_s, double* out_f
     MP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     DevBuf sink;
     MP_TRY(sink.alloc(64));
-    cudaEvent_t e0, e1;
-    MP_CUDA_TRY(cudaEventCreate(&e0));
-    MP_CUDA_TRY(cudaEventCreate(&e1));
+    EventTimer timer;
     float ms = 0;
     {
         const int iters = 16384, threads = 512, blocks = sms * 2;
         k_imad_wide<<<blocks, threads>>>(sink.as<uint32_t>(), 3, 5, iters);  // warm-up (also ramps the clocks)
         double best = 0;
         for (int rep = 0; rep < 5; rep++) {
-            MP_CUDA_TRY(cudaEventRecord(e0));
+            MP_TRY(timer.start(0));
             k_imad_wide<<<blocks, threads>>>(sink.as<uint32_t>(), 3, 5, iters);
-            MP_CUDA_TRY(cudaEventRecord(e1));
-            MP_CUDA_TRY(cudaEventSynchronize(e1));
-            MP_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            MP_TRY(timer.stop(0));
+            MP_TRY(timer.elapsed_ms(&ms));
             double rate = (double)blocks * threads * iters * 32.0 / (ms * 1e-3);
             if (rate > best) best = rate;
         }
@@ -196,18 +193,15 @@ int mp_debug_int_pipe_rate(int device, double* out_wide_mac_per_s, double* out_f
         k_fq_mul_rate<<<blocks, threads>>>(sink.as<uint32_t>(), iters);
         double best = 0;
         for (int rep = 0; rep < 5; rep++) {
-            MP_CUDA_TRY(cudaEventRecord(e0));
+            MP_TRY(timer.start(0));
             k_fq_mul_rate<<<blocks, threads>>>(sink.as<uint32_t>(), iters);
-            MP_CUDA_TRY(cudaEventRecord(e1));
-            MP_CUDA_TRY(cudaEventSynchronize(e1));
-            MP_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            MP_TRY(timer.stop(0));
+            MP_TRY(timer.elapsed_ms(&ms));
             double rate = (double)blocks * threads * iters * 2.0 / (ms * 1e-3);
             if (rate > best) best = rate;
         }
         if (out_fq_mul_per_s) *out_fq_mul_per_s = best;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     MP_KERNEL_CHECK();
     return MP_OK;
 }

@@ -468,21 +468,17 @@ extern "C" int mp_ntt(int device, uint64_t* data, unsigned log_n, int inverse, i
     MP_TRY(c.alloc(bytes));
     MP_CUDA_TRY(cudaMemcpy(a.p, data, bytes, cudaMemcpyHostToDevice));
     MP_TRY(fr_to_mont(a.p, a.p, d.n, 0));
-    cudaEvent_t e0, e1;
-    MP_CUDA_TRY(cudaEventCreate(&e0));
-    MP_CUDA_TRY(cudaEventCreate(&e1));
-    MP_CUDA_TRY(cudaEventRecord(e0, 0));
+    EventTimer timer;
+    MP_TRY(timer.start(0));
     const void* pre = (!inverse && coset) ? d.pre_coset.p : nullptr;
     const void* post = (inverse && coset) ? d.post_coset_inv.p : nullptr;
     const void* post_c = (inverse && !coset) ? d.post_inv.p : nullptr;
     MP_TRY(ntt_run(d, inverse != 0, a.p, b.p, c.p, 1, pre, post, post_c, 0));
-    MP_CUDA_TRY(cudaEventRecord(e1, 0));
+    MP_TRY(timer.stop(0));
     MP_TRY(fr_from_mont(b.p, b.p, d.n, 0));
     MP_CUDA_TRY(cudaMemcpy(data, b.p, bytes, cudaMemcpyDeviceToHost));
     float ms = 0;
-    MP_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    MP_TRY(timer.elapsed_ms(&ms));
     if (out_ms) *out_ms = ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     return MP_OK;
 }

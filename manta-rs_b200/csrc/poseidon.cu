@@ -78,10 +78,8 @@ extern "C" int mp_poseidon_permute(int device, int width, int full_rounds, int p
     MP_CUDA_TRY(cudaMemcpy(d_st.p, states, count * width * 32, cudaMemcpyHostToDevice));
     k_fr_to_mont_inplace<<<div_up(n_rk + n_mds, 128), 128>>>(d_par.as<uint32_t>(), n_rk + n_mds);
     MP_KERNEL_CHECK();
-    cudaEvent_t e0, e1;
-    MP_CUDA_TRY(cudaEventCreate(&e0));
-    MP_CUDA_TRY(cudaEventCreate(&e1));
-    MP_CUDA_TRY(cudaEventRecord(e0, 0));
+    EventTimer timer;
+    MP_TRY(timer.start(0));
     const uint32_t* rk = d_par.as<uint32_t>();
     const uint32_t* md = rk + n_rk * 8;
     uint32_t* st = d_st.as<uint32_t>();
@@ -96,12 +94,10 @@ extern "C" int mp_poseidon_permute(int device, int width, int full_rounds, int p
         default: launch_poseidon<8>(rk, md, st, count, hf, partial_rounds); break;
     }
     MP_KERNEL_CHECK();
-    MP_CUDA_TRY(cudaEventRecord(e1, 0));
+    MP_TRY(timer.stop(0));
     MP_CUDA_TRY(cudaMemcpy(states, d_st.p, count * width * 32, cudaMemcpyDeviceToHost));
     float ms = 0;
-    MP_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    MP_TRY(timer.elapsed_ms(&ms));
     if (out_device_ms) *out_device_ms = ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     return MP_OK;
 }

@@ -76,6 +76,8 @@ struct mp_batch {
     MsmSortWs rc_a, rc_b, rc_b2, rc_l, rc_h;  // B1 and B2 keep separate row/column lists: they may run on different streams
     bool use_ba = false;
     DevBuf res_g1, res_g2, red_a, red_b1, red_l, red_h, red_b2, proofs;
+    DevBuf bad_dev;                // 1 + index of the first proof with a non-canonical scalar (k_prove_prep)
+    uint32_t* bad_host = nullptr;  // pinned copy, read after the streams drain
     MsmGeom gz{}, gh{};
     cudaEvent_t ev[PH_COUNT + 1] = {};
     float phase_ms[PH_COUNT] = {};
@@ -89,15 +91,24 @@ namespace mp {
 // kernels
 // ---------------------------------------------------------------------------------------------------------
 // z' extras and the Montgomery copy of z used by the R1CS evaluation.  rs: [batch][2][8] canonical.
-__global__ void k_prove_prep(uint32_t* z_canon, uint32_t* z_mont, const uint32_t* __restrict__ rs, uint32_t n, uint32_t zlen) {
+// Scalars cross the ABI canonical (< r): anything else would be recoded with a dropped carry and yield a wrong proof, so the
+// first offending proof is reported through `bad` (1 + proof index; 0 = all fine) and the call fails with MP_ERR_INVALID_ARG.
+MP_DEV bool fr_is_canonical(const Fr& x) {
+    uint32_t t[Fr::N];
+    return Fr::sub_raw(t, x.l, FrParams::mod()) != 0;  // borrow <=> x < r
+}
+__global__ void k_prove_prep(uint32_t* z_canon, uint32_t* z_mont, const uint32_t* __restrict__ rs, uint32_t n, uint32_t zlen, uint32_t* bad) {
     const uint32_t b = blockIdx.y;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t* zc = z_canon + (size_t)b * zlen * 8;
     uint32_t* zm = z_mont + (size_t)b * zlen * 8;
     if (i < n) {
-        Fr::load(zc + (size_t)i * 8).to_mont().store(zm + (size_t)i * 8);
+        const Fr v = Fr::load(zc + (size_t)i * 8);
+        if (!fr_is_canonical(v)) atomicMax(bad, b + 1);
+        v.to_mont().store(zm + (size_t)i * 8);
     } else if (i == n) {
         Fr r = Fr::load(rs + (size_t)b * 16), s = Fr::load(rs + (size_t)b * 16 + 8);
+        if (!fr_is_canonical(r) || !fr_is_canonical(s)) atomicMax(bad, b + 1);
         r.store(zc + (size_t)n * 8);
         s.store(zc + (size_t)(n + 1) * 8);
         // -(r s) canonical: mont(r) * s = r*s (canonical), then negate
@@ -387,6 +398,9 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch*
     MP_TRY(b->red_h.alloc(msm_reduce_scratch_bytes(b->gh, cap, false)));
     MP_TRY(b->red_b2.alloc(msm_reduce_scratch_bytes(b->gz, cap, true)));
     MP_TRY(b->proofs.alloc(cap * MP_PROOF_BYTES));
+    MP_TRY(b->bad_dev.alloc(4));
+    MP_CUDA_TRY(cudaHostAlloc((void**)&b->bad_host, 4, cudaHostAllocDefault));
+    *b->bad_host = 0;
     return MP_OK;
 }
 
@@ -404,9 +418,11 @@ static int batch_enqueue(mp_batch* b) {
     cudaStream_t st_tail = b->overlap ? b->st2 : st;  // stream of the G2 reduction tail
     if (c->last_heavy && c->last_heavy_owner != b) MP_CUDA_TRY(cudaStreamWaitEvent(st, c->last_heavy, 0));
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_PREP], st));
+    MP_CUDA_TRY(cudaMemsetAsync(b->bad_dev.p, 0, 4, st));
     k_prove_prep<<<dim3(div_up(c->n + 1, 256), (unsigned)cnt), 256, 0, st>>>(b->z_canon.as<uint32_t>(), b->z_mont.as<uint32_t>(),
-                                                                           b->rs.as<uint32_t>(), (uint32_t)c->n, c->zlen);
+                                                                           b->rs.as<uint32_t>(), (uint32_t)c->n, c->zlen, b->bad_dev.as<uint32_t>());
     MP_KERNEL_CHECK();
+    MP_CUDA_TRY(cudaMemcpyAsync(b->bad_host, b->bad_dev.p, 4, cudaMemcpyDeviceToHost, st));
     char* res1 = b->res_g1.as<char>();
     char* rrc1 = b->resrc_g1.as<char>();
     MsmJob g1[4] = {
@@ -481,6 +497,11 @@ static int batch_finalize(mp_batch* b, float* out_ms) {
     MP_CUDA_TRY(cudaEventElapsedTime(&total, b->ev[PH_PREP], b->ev[PH_COUNT]));
     b->ran = true;
     if (out_ms) *out_ms = total;
+    if (*b->bad_host) {
+        set_error_detail("proof %u of the batch carries a non-canonical scalar (z, r or s >= the Fr modulus)", *b->bad_host - 1);
+        b->ran = false;
+        return MP_ERR_INVALID_ARG;
+    }
     return MP_OK;
 }
 
@@ -558,7 +579,11 @@ int mp_ctx_info(const mp_ctx* ctx, uint64_t* n_vars, uint64_t* n_instance, uint6
 int mp_batch_create(mp_ctx* ctx, size_t capacity, mp_batch** out) { return mp_batch_create_ex(ctx, capacity, 0, out); }
 
 int mp_batch_create_ex(mp_ctx* ctx, size_t capacity, int high_priority, mp_batch** out) {
-    if (!ctx || !out || capacity == 0 || capacity > 60000) return MP_ERR_INVALID_ARG;
+    if (!ctx || !out || capacity == 0) return MP_ERR_INVALID_ARG;
+    if (capacity > MP_MAX_BATCH) {  // the NTT launches carry 3 * count vectors in gridDim.y (<= 65535)
+        mp::set_error_detail("batch capacity %zu exceeds %d", capacity, MP_MAX_BATCH);
+        return MP_ERR_UNSUPPORTED;
+    }
     mp_batch* b = new (std::nothrow) mp_batch();
     if (!b) return MP_ERR_OOM;
     int rc = batch_create_impl(ctx, capacity, high_priority, b);
@@ -577,11 +602,14 @@ void mp_batch_destroy(mp_batch* b) {
     if (b->st2) cudaStreamSynchronize(b->st2);
     for (auto& e : b->ev)
         if (e) cudaEventDestroy(e);
-    if (b->ctx && b->ctx->last_heavy_owner == b) {
+    if (b->ctx) {
         std::lock_guard<std::mutex> lock(b->ctx->mu);
-        b->ctx->last_heavy = nullptr;
-        b->ctx->last_heavy_owner = nullptr;
+        if (b->ctx->last_heavy_owner == b) {
+            b->ctx->last_heavy = nullptr;
+            b->ctx->last_heavy_owner = nullptr;
+        }
     }
+    if (b->bad_host) cudaFreeHost(b->bad_host);
     for (cudaEvent_t e : {b->ev_g2_heavy, b->ev_g2, b->ev_heavy, b->ev_tail_fork, b->ev_sort_b, b->ev_dom0, b->ev_dom1})
         if (e) cudaEventDestroy(e);
     if (b->st) cudaStreamDestroy(b->st);
@@ -695,7 +723,7 @@ int mp_prove_batch(mp_ctx* ctx, size_t count, const uint64_t* z, const uint64_t*
     size_t chunk = 128;
     if (const char* e = getenv("MP_PROVE_BATCH_CHUNK")) {  // test hook / memory knob
         long v = atol(e);
-        if (v >= 1 && v <= 60000) chunk = (size_t)v;
+        if (v >= 1 && v <= MP_MAX_BATCH) chunk = (size_t)v;
     }
     if (count < chunk) chunk = count;
     mp_batch* b = nullptr;
@@ -724,6 +752,16 @@ int mp_prove(mp_ctx* ctx, const uint64_t* z, const uint64_t r[4], const uint64_t
     MP_TRY(mp_batch_upload(ctx->single, 1, z, r, s));
     MP_TRY(mp_batch_run(ctx->single, nullptr));
     return mp_batch_download(ctx->single, out_proof);
+}
+
+int mp_debug_prove_ba_demand(uint32_t n_vars, uint32_t domain_size, size_t capacity, size_t count, int g2, uint64_t out[4]) {
+    if (!out || !n_vars || !domain_size || !capacity || count > capacity) return MP_ERR_INVALID_ARG;
+    const uint32_t zlen = n_vars + N_EXTRA;
+    MsmGeom gz = msm_geom(PROVE_C, 1, zlen, zlen, capacity * 2), gh = msm_geom(PROVE_C, 1, domain_size, domain_size, capacity * 2);
+    const MsmGeom g1[4] = {gz, gz, gz, gh};
+    if (g2) msm_ba_ws_demand(&gz, 1, capacity, count, out);
+    else msm_ba_ws_demand(g1, 4, capacity, count, out);
+    return MP_OK;
 }
 
 int mp_witness_map(mp_ctx* ctx, const uint64_t* z, uint64_t* out_h) {
