@@ -131,6 +131,7 @@ MP_API const char* mp_phase_name(int i);
  * accumulations): its CUDA-event time and the number of affine additions it performed (5 Fq multiplications each). */
 MP_API int mp_batch_dominant_kernel(mp_batch* b, float* out_ms, uint64_t* out_additions);
 MP_API uint64_t mp_batch_kernel_launches(const mp_batch* b); /* kernels launched by the last mp_batch_run */
+MP_API uint64_t mp_batch_device_bytes(const mp_batch* b);    /* device memory held by the batch object (all of it is allocated at creation) */
 /* overlap = 1 (default): the latency-bound tail of the G2 reduction (for batches of <= 16 proofs the whole G2 MSM) runs on a
  * second stream next to the witness map and the G1 MSMs; overlap = 0:
  * every kernel on one stream in program order, so the per-phase CUDA-event times are those of the kernels alone. */
@@ -142,6 +143,14 @@ MP_API int mp_msm_g1(int device, const uint8_t* bases /* n x 96 */, const uint64
               uint8_t out_point[MP_G1_BYTES], float* out_device_ms);
 MP_API int mp_msm_g2(int device, const uint8_t* bases /* n x 192 */, const uint64_t* scalars, size_t n,
               uint8_t out_point[MP_G2_BYTES], float* out_device_ms);
+/* The same MSM against bases that stay resident on the device (proving keys and ceremony powers are fixed; only the
+ * scalars change per call): create uploads the bases, converts them to Montgomery form and precomputes the window rows
+ * 2^(c t) P_i that fit MP_MSM_TABLE_LIMIT_MB (default 8192) of device memory, run moves n <= n_bases scalars (the rest count
+ * as zero, ark's `size = min(bases, scalars)`) and returns the uncompressed result.  group: 1 = G1, 2 = G2. */
+typedef struct mp_msm_bases mp_msm_bases;
+MP_API int mp_msm_bases_create(int device, int group, const uint8_t* bases, size_t n, mp_msm_bases** out);
+MP_API int mp_msm_bases_run(mp_msm_bases* h, const uint64_t* scalars, size_t n, uint8_t* out_point, float* out_device_ms);
+MP_API void mp_msm_bases_destroy(mp_msm_bases* h);
 /* Sum of n affine points (ark uncompressed in, ark uncompressed out).  Combines the per-GPU partial results of one
  * large MSM sharded by base range (the only exchange step of the path, 96 / 192 bytes per GPU). */
 MP_API int mp_points_sum_g1(int device, const uint8_t* points /* n x 96 */, size_t n, uint8_t out_point[MP_G1_BYTES]);

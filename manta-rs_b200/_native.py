@@ -62,9 +62,13 @@ SYMBOLS = {
     "mp_phase_name": (ctypes.c_char_p, [_I]),
     "mp_batch_dominant_kernel": (_I, [_V, _V, _V]),
     "mp_batch_kernel_launches": (ctypes.c_uint64, [_V]),
+    "mp_batch_device_bytes": (ctypes.c_uint64, [_V]),
     "mp_batch_set_overlap": (_I, [_V, _I]),
     "mp_msm_g1": (_I, [_I, _V, _V, _SZ, _V, _V]),
     "mp_msm_g2": (_I, [_I, _V, _V, _SZ, _V, _V]),
+    "mp_msm_bases_create": (_I, [_I, _I, _V, _SZ, _V]),
+    "mp_msm_bases_run": (_I, [_V, _V, _SZ, _V, _V]),
+    "mp_msm_bases_destroy": (None, [_V]),
     "mp_points_sum_g1": (_I, [_I, _V, _SZ, _V]),
     "mp_points_sum_g2": (_I, [_I, _V, _SZ, _V]),
     "mp_ntt": (_I, [_I, _V, _U, _I, _I, _V]),

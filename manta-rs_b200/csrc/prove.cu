@@ -83,6 +83,7 @@ struct mp_batch {
     float phase_ms[PH_COUNT] = {};
     uint64_t launches = 0;
     bool ran = false, in_flight = false, upload_timed = false;
+    size_t device_bytes = 0;  // device memory behind this batch object (every per-proof buffer is allocated at creation)
 };
 
 namespace mp {
@@ -332,6 +333,8 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch*
     MP_TRY(use_device(c->device));
     b->ctx = c;
     b->capacity = cap;
+    size_t free0 = 0, free1 = 0, total_mem = 0;
+    MP_CUDA_TRY(cudaMemGetInfo(&free0, &total_mem));
     int prio_least = 0, prio_greatest = 0;
     MP_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
     const int prio = high_priority ? prio_greatest : prio_least;
@@ -401,6 +404,8 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch*
     MP_TRY(b->bad_dev.alloc(4));
     MP_CUDA_TRY(cudaHostAlloc((void**)&b->bad_host, 4, cudaHostAllocDefault));
     *b->bad_host = 0;
+    MP_CUDA_TRY(cudaMemGetInfo(&free1, &total_mem));
+    b->device_bytes = free0 > free1 ? free0 - free1 : 0;
     return MP_OK;
 }
 
@@ -708,6 +713,7 @@ int mp_batch_dominant_kernel(mp_batch* b, float* out_ms, uint64_t* out_additions
 const char* mp_phase_name(int i) { return (i >= 0 && i < PH_COUNT) ? kPhaseNames[i] : ""; }
 
 uint64_t mp_batch_kernel_launches(const mp_batch* b) { return b ? b->launches : 0; }
+uint64_t mp_batch_device_bytes(const mp_batch* b) { return b ? b->device_bytes : 0; }
 
 int mp_batch_set_overlap(mp_batch* b, int overlap) {
     if (!b) return MP_ERR_INVALID_ARG;

@@ -26,7 +26,7 @@ def _batch_inv(vals, r):
     return out
 
 
-def qap_at_tau(cs, tau, root_of_unity_2_32=None):
+def _qap_at_tau(cs, tau, root_of_unity_2_32=None):
     """u_i(tau), v_i(tau), w_i(tau) for all variables, Z(tau), m  (SURVEY.md C.7)."""
     r = cs.modulus
     m, log_m = cs.m, cs.log_m
@@ -66,10 +66,10 @@ def _fixed_base(group: int, scalars, device: int) -> bytes:
 
 
 def generate(cs, trapdoor, device: int = 0, h_len=None):
-    """Returns (proving-key bytes in `ProvingContext` format, trapdoor dict)."""
+    """Returns the proving-key bytes in `ProvingContext` format."""
     tau, alpha, beta, gamma, delta = trapdoor
     r = cs.modulus
-    u, v, w, zt = qap_at_tau(cs, tau)
+    u, v, w, zt = _qap_at_tau(cs, tau)
     n, p, m = cs.n, cs.p, cs.m
     h_len = m - 1 if h_len is None else h_len
     ginv, dinv = pow(gamma, -1, r), pow(delta, -1, r)
@@ -105,23 +105,4 @@ def generate(cs, trapdoor, device: int = 0, h_len=None):
     b2_q = g2[3 * P2:]
     pk = (alpha_g1 + beta_g2 + gamma_g2 + delta_g2 + vec(gamma_abc, p) + beta_g1 + delta_g1 + vec(a_q, n)
           + vec(b1_q, n) + vec(b2_q, n) + vec(h_q, h_len) + vec(l_q, n - p))
-    trap = dict(tau=tau, alpha=alpha, beta=beta, gamma=gamma, delta=delta, u=u, v=v, w=w, zt=zt)
-    return pk, trap
-
-
-def trapdoor_proof_scalars(cs, trap, z, r_rand, s_rand):
-    """Discrete logs (a, b, c) of the proof elements w.r.t. the generators (closed form)."""
-    r = cs.modulus
-    u, v, w = trap["u"], trap["v"], trap["w"]
-    al, be, de, zt = trap["alpha"], trap["beta"], trap["delta"], trap["zt"]
-    n, p = cs.n, cs.p
-    At = sum(z[i] * u[i] for i in range(n)) % r
-    Bt = sum(z[i] * v[i] for i in range(n)) % r
-    Ct = sum(z[i] * w[i] for i in range(n)) % r
-    a_s = (al + At + r_rand * de) % r
-    b_s = (be + Bt + s_rand * de) % r
-    ht = (At * Bt - Ct) * pow(zt, -1, r) % r
-    dinv = pow(de, -1, r)
-    c_s = (sum(z[i] * (be * u[i] + al * v[i] + w[i]) for i in range(p, n)) * dinv + ht * zt * dinv
-           + s_rand * a_s + r_rand * b_s - r_rand * s_rand * de) % r
-    return a_s, b_s, c_s
+    return pk

@@ -379,44 +379,50 @@ static uint64_t scalar_window(const uint64_t* s, int start, int c) {  // (s >> s
     return (uint64_t)(v >> o) & (((uint64_t)1 << c) - 1);
 }
 
+// One window of ark's `multi_scalar_mul`: buckets of the c-bit digit starting at bit w_start, then the running-sum fold.
 template <class F>
-static Jac<F> msm(const AffineT<F>* bases, const uint64_t* scalars, size_t n_bases, size_t n_scalars, int threads) {
-    size_t size = std::min(n_bases, n_scalars);
-    const int c = ark_window(size);
-    const int num_bits = 255;
-    std::vector<int> starts;
-    for (int s = 0; s < num_bits; s += c) starts.push_back(s);
-    std::vector<Jac<F>> window_sums(starts.size());
-#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) if (threads > 1)
-    for (size_t wi = 0; wi < starts.size(); wi++) {
-        const int w_start = starts[wi];
-        Jac<F> res = Jac<F>::identity();
-        std::vector<Jac<F>> buckets(((size_t)1 << c) - 1, Jac<F>::identity());
-        for (size_t i = 0; i < size; i++) {
-            const uint64_t* s = scalars + 4 * i;
-            if (scalar_is_zero(s)) continue;
-            if (scalar_is_one(s)) {
-                if (w_start == 0) res.add_mixed(bases[i]);
-            } else {
-                uint64_t d = scalar_window(s, w_start, c);
-                if (d) buckets[d - 1].add_mixed(bases[i]);
-            }
+static Jac<F> msm_window(const AffineT<F>* bases, const uint64_t* scalars, size_t size, int c, int w_start) {
+    Jac<F> res = Jac<F>::identity();
+    std::vector<Jac<F>> buckets(((size_t)1 << c) - 1, Jac<F>::identity());
+    for (size_t i = 0; i < size; i++) {
+        const uint64_t* s = scalars + 4 * i;
+        if (scalar_is_zero(s)) continue;
+        if (scalar_is_one(s)) {
+            if (w_start == 0) res.add_mixed(bases[i]);
+        } else {
+            uint64_t d = scalar_window(s, w_start, c);
+            if (d) buckets[d - 1].add_mixed(bases[i]);
         }
-        Jac<F> running = Jac<F>::identity();
-        for (size_t b = buckets.size(); b-- > 0;) {
-            running.add(buckets[b]);
-            res.add(running);
-        }
-        window_sums[wi] = res;
     }
+    Jac<F> running = Jac<F>::identity();
+    for (size_t b = buckets.size(); b-- > 0;) {
+        running.add(buckets[b]);
+        res.add(running);
+    }
+    return res;
+}
+// ... and the combination of the window sums: lowest + sum_{w >= 1} 2^(c w) window_sums[w] by Horner
+template <class F>
+static Jac<F> msm_combine(const std::vector<Jac<F>>& window_sums, int c) {
     Jac<F> lowest = window_sums[0];
     Jac<F> total = Jac<F>::identity();
-    for (size_t wi = starts.size() - 1; wi >= 1; wi--) {
+    for (size_t wi = window_sums.size() - 1; wi >= 1; wi--) {
         total.add(window_sums[wi]);
         for (int k = 0; k < c; k++) total.dbl_in_place();
     }
     lowest.add(total);
     return lowest;
+}
+static int msm_num_windows(int c) { return (255 + c - 1) / c; }
+
+template <class F>
+static Jac<F> msm(const AffineT<F>* bases, const uint64_t* scalars, size_t n_bases, size_t n_scalars, int threads) {
+    size_t size = std::min(n_bases, n_scalars);
+    const int c = ark_window(size);
+    std::vector<Jac<F>> window_sums(msm_num_windows(c));
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) if (threads > 1)
+    for (size_t wi = 0; wi < window_sums.size(); wi++) window_sums[wi] = msm_window<F>(bases, scalars, size, c, (int)wi * c);
+    return msm_combine<F>(window_sums, c);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -545,20 +551,36 @@ static void create_proof(const OracleCtx& c, const uint64_t* z_canon, const uint
     G1J h_acc, l_acc, a_acc, b1_acc;
     G2J b2_acc;
     bool r_zero = scalar_is_zero(r);
-    const int inner = std::max(1, threads);
-#pragma omp parallel sections num_threads(std::min(threads, 5)) if (threads > 1)
-    {
-#pragma omp section
-        h_acc = msm<Fq>(c.h_query.data(), h_canon.data(), c.h_query.size(), h.size(), inner);
-#pragma omp section
-        l_acc = msm<Fq>(c.l_query.data(), aux, c.l_query.size(), c.w, inner);
-#pragma omp section
-        a_acc = msm<Fq>(c.a_query.data() + 1, assignment, n - 1, n - 1, inner);
-#pragma omp section
-        { if (!r_zero) b1_acc = msm<Fq>(c.b_g1_query.data() + 1, assignment, n - 1, n - 1, inner); }
-#pragma omp section
-        b2_acc = msm<Fq2>(c.b_g2_query.data() + 1, assignment, n - 1, n - 1, inner);
+    // The five multi_scalar_mul calls of create_proof.  threads > 1 mirrors arkworks' `parallel` feature with ONE flat task
+    // list over (MSM, window) - 5 x ~20 windows, the G2 windows (3x the cost) first - so that every host thread stays busy;
+    // the window sums are combined exactly as the serial code does, so the result is the same group element.
+    const size_t nh = std::min(c.h_query.size(), h.size()), nz = n - 1;
+    const int ch = ark_window(nh), cl = ark_window(std::min<size_t>(c.l_query.size(), c.w)), cz = ark_window(nz);
+    std::vector<G1J> wh(msm_num_windows(ch)), wl(msm_num_windows(cl)), wa(msm_num_windows(cz)), wb1(r_zero ? 0 : msm_num_windows(cz));
+    std::vector<G2J> wb2(msm_num_windows(cz));
+    struct Task { int msm, w; };
+    std::vector<Task> tasks;
+    for (size_t w = 0; w < wb2.size(); w++) tasks.push_back({4, (int)w});
+    for (size_t w = 0; w < wh.size(); w++) tasks.push_back({0, (int)w});
+    for (size_t w = 0; w < wl.size(); w++) tasks.push_back({1, (int)w});
+    for (size_t w = 0; w < wa.size(); w++) tasks.push_back({2, (int)w});
+    for (size_t w = 0; w < wb1.size(); w++) tasks.push_back({3, (int)w});
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) if (threads > 1)
+    for (size_t t = 0; t < tasks.size(); t++) {
+        const int w = tasks[t].w;
+        switch (tasks[t].msm) {
+            case 0: wh[w] = msm_window<Fq>(c.h_query.data(), h_canon.data(), nh, ch, w * ch); break;
+            case 1: wl[w] = msm_window<Fq>(c.l_query.data(), aux, std::min<size_t>(c.l_query.size(), c.w), cl, w * cl); break;
+            case 2: wa[w] = msm_window<Fq>(c.a_query.data() + 1, assignment, nz, cz, w * cz); break;
+            case 3: wb1[w] = msm_window<Fq>(c.b_g1_query.data() + 1, assignment, nz, cz, w * cz); break;
+            default: wb2[w] = msm_window<Fq2>(c.b_g2_query.data() + 1, assignment, nz, cz, w * cz); break;
+        }
     }
+    h_acc = msm_combine<Fq>(wh, ch);
+    l_acc = msm_combine<Fq>(wl, cl);
+    a_acc = msm_combine<Fq>(wa, cz);
+    if (!r_zero) b1_acc = msm_combine<Fq>(wb1, cz);
+    b2_acc = msm_combine<Fq2>(wb2, cz);
     // calculate_coeff(initial, query, vk_param, assignment) = initial + query[0] + acc + vk_param
     G1J delta1 = from_affine(c.delta_g1);
     G1J g_a = delta1.mul(r, 4);
@@ -601,7 +623,7 @@ extern "C" {
 
 int oracle_max_threads() {
 #ifdef _OPENMP
-    return omp_get_max_threads();
+    return omp_get_num_procs();  // the host's cores (affinity-aware), NOT OMP_NUM_THREADS: torchrun exports OMP_NUM_THREADS=1
 #else
     return 1;
 #endif

@@ -168,6 +168,56 @@ def test_points_sum_and_sharded_msm(native, group):
     assert sharded._native_sum(group, 0)(inf + parts[:pb] + inf, 3) == parts[:pb]
 
 
+@pytest.mark.parametrize("group,n", [(1, 3000), (2, 700), (1, 5)])
+def test_msm_resident_bases(native, group, n):
+    """Bases resident on the device (mp_msm_bases_*): several scalar vectors against one handle, fewer scalars than bases
+    (ark: size = min(bases, scalars)), and an empty call; with and without room for the precomputed window rows."""
+    lib = native.lib()
+    rng = random.Random(50 + group + n)
+    pb = 96 * group
+    bases = cref.fixed_base(group, [rng.randrange(1, C.r) for _ in range(n)])
+    for limit in (None, "0"):
+        if limit is not None:
+            os.environ["MP_MSM_TABLE_LIMIT_MB"] = limit     # no precomputed rows: one bucket set per window + Horner
+        try:
+            h = ctypes.c_void_p()
+            _chk(native, lib.mp_msm_bases_create(0, group, bases, n, ctypes.byref(h)))
+        finally:
+            os.environ.pop("MP_MSM_TABLE_LIMIT_MB", None)
+        for cnt in (n, n, n // 2, 1, 0):
+            sc = [rng.randrange(C.r) for _ in range(cnt)]
+            out = ctypes.create_string_buffer(pb)
+            ms = ctypes.c_float()
+            _chk(native, lib.mp_msm_bases_run(h, native.pack_scalars(sc), cnt, out, ctypes.byref(ms)))
+            assert out.raw == cref.msm(group, bases[:cnt * pb], sc, threads=8), (group, n, cnt, limit)
+        assert lib.mp_msm_bases_run(h, native.pack_scalars([1] * (n + 1)), n + 1, out, None) == 1   # more scalars than bases
+        lib.mp_msm_bases_destroy(h)
+
+
+def test_non_canonical_scalars_are_rejected(native):
+    """z, r, s cross the ABI canonical (< r); a value >= r fails the call instead of yielding a wrong proof."""
+    from manta_rs_b200 import groth16 as g16
+    cs = wl.make_r1cs(3, 40)
+    pk, trap = oracle_keygen(cs, wl.sample_trapdoor(13))
+    ctx = g16.ProvingContext.decode(pk)
+    z = wl.make_assignment(cs, 1)
+    h = ctx.native(g16.R1CS.from_workload(cs, z).matrices)
+    out = ctypes.create_string_buffer(192)
+    lib = native.lib()
+    raw = lambda vals: b"".join(int(v).to_bytes(32, "little") for v in vals)
+    assert lib.mp_prove(h, raw(z), raw([5]), raw([6]), out) == 0
+    assert out.raw == trapdoor_proof_bytes(cs, trap, z, 5, 6)
+    bad = list(z)
+    bad[7] = C.r                                     # the modulus itself
+    assert lib.mp_prove(h, raw(bad), raw([5]), raw([6]), out) == 1
+    assert b"non-canonical" in lib.mp_last_error_detail()
+    assert lib.mp_prove(h, raw(z), raw([(1 << 256) - 1]), raw([6]), out) == 1
+    assert lib.mp_prove(h, raw(z), raw([5]), raw([C.r + 1]), out) == 1
+    assert lib.mp_prove(h, raw(z), raw([C.r - 1]), raw([C.r - 1]), out) == 0   # the largest canonical values still prove
+    assert out.raw == trapdoor_proof_bytes(cs, trap, z, C.r - 1, C.r - 1)
+    ctx.close()
+
+
 def test_prove_batch_is_chunked(native, monkeypatch):
     """mp_prove_batch reuses one bounded batch object over chunks of the request (here 5 proofs in chunks of 2)."""
     from manta_rs_b200 import groth16 as g16
@@ -368,7 +418,9 @@ def test_prove_reference_shapes_full_size(native, shape, dist):
     every proof against the trapdoor closed form and the first against the full CPU oracle."""
     from manta_rs_b200 import groth16 as g16, keygen
     cs = wl.make_shape(shape, dist=dist)
-    pk, trap = keygen.generate(cs, wl.sample_trapdoor(21))
+    from oracle import trapdoor
+    pk = keygen.generate(cs, wl.sample_trapdoor(21))
+    _, _, trap = trapdoor.key_scalars(cs, wl.sample_trapdoor(21))   # the oracle's own QAP evaluation
     # spot-check the GPU-generated key against the oracle's fixed-base results
     r = cs.modulus
     pos_a = 96 + 192 * 3 + 8 + 96 * cs.p + 96 * 2 + 8

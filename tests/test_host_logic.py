@@ -206,3 +206,19 @@ def test_batched_affine_round_scratch_covers_every_partial_batch():
                     worst = max(worst, need_threads / have_threads)
                 assert worst == 1.0, (name, cap, g2, worst)   # the bound is tight: some count needs exactly the provisioned slots
     assert lib.mp_debug_prove_ba_demand(35175, 1 << 16, 4, 5, 0, out) == 1
+
+
+def test_bench_helpers_scalars_credit_and_dot():
+    """Host-side helpers of bench.py: uniform canonical scalars, the reference's window rule behind the credited work
+    (SURVEY.md 8d figures), and the closed-form dot product."""
+    import bench
+    r = bench.FR
+    buf = bench.random_scalars(5000, 3)
+    vals = bench.unpack_fr(buf)
+    assert len(vals) == 5000 and all(v < r for v in vals) and max(vals) > r // 2 and len(set(vals)) == 5000
+    assert bench.random_scalars(5000, 3) == buf and bench.random_scalars(10, 4) != buf[:320]
+    assert [bench.ark_window(1 << k) for k in (16, 18, 20, 22, 24)] == [13, 14, 15, 17, 18] and bench.ark_window(31) == 3
+    assert bench.credited_msm_fq_muls(1 << 16) == 14417920 and bench.credited_msm_fq_muls(1 << 20) == 196083712   # 14.42 M / 196.1 M
+    assert bench.credited_msm_fq_muls(1 << 24) == 2768240640 and bench.credited_msm_fq_muls(1 << 20, True) == 3 * 196083712
+    other = bench.random_scalars(5000, 5)
+    assert bench.dot_mod(buf, other, r) == sum(a * b for a, b in zip(vals, bench.unpack_fr(other))) % r

@@ -36,6 +36,14 @@ def _worker(rank, world, port, total):
     gathered = bench.gather_proofs(local, total, rank, world, device="cpu")
     t = bench.max_over_ranks(float(rank + 1), device="cpu")
     assert t == float(world)
+    # rank-major exchange used by the parity check of a gathered step: record j of rank r belongs to global proof r + j * world
+    recs = b"".join(int(idx).to_bytes(4, "little") for idx in mine).ljust(4 * ((total + world - 1) // world), b"\xff")
+    by_rank = bench.gather_by_rank(recs, rank, world, device="cpu")
+    if rank == 0:
+        for idx in range(total):
+            assert int.from_bytes(by_rank[idx % world][4 * (idx // world):4 * (idx // world) + 4], "little") == idx
+    else:
+        assert by_rank is None
     if rank == 0:
         assert gathered.shape == (total, 192)
         for idx in range(total):
