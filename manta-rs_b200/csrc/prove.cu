@@ -49,6 +49,7 @@ struct mp_ctx {
     DevBuf tab_a, tab_b1, tab_l, tab_h, tab_b2;
     DevBuf valid_a, valid_b, valid_l, valid_h;  // per-table "base is not infinity" bitmaps
     size_t device_bytes = 0;
+    bool glv = true;               // every A / B1 query point lies in the prime-order subgroup: the finishing kernel may use the GLV ladder
     std::mutex mu;
     std::mutex single_mu;          // serialises mp_prove callers on the cached one-proof batch
     mp_batch* single = nullptr;   // lazily created capacity-1 batch behind mp_prove
@@ -133,17 +134,116 @@ MP_COLD XYZZ<F> scalar_mul_affine(const Affine<F>& p, const uint32_t* k) {
     return r;
 }
 
-// k * P on G1 with the GLV endomorphism phi(x, y) = (beta x, y) = lambda P (lambda = z^2 - 1, 128 bits): k = k2 lambda + k1 by
-// plain integer division (both halves < 2^128 because lambda^2 ~ r), then one 128-step double-and-add over
-// {P, phi(P), P + phi(P)}: 128 doublings + ~96 additions instead of 255 + ~128.  The two scalar multiplications of the
-// finishing kernel are serial single-lane chains, so this is latency, not throughput.  Valid for points of the prime-order
-// subgroup (MSM results over a well-formed proving key always are); the scalar multiplication of ark-groth16 agrees there.
-MP_COLD XYZZ<Fq> scalar_mul_glv(const Affine<Fq>& p, const uint32_t* k) {
-    if (p.is_inf()) return XYZZ<Fq>::inf();
-    // long division of the 255-bit k by lambda: quotient k2, remainder k1
-    uint32_t rem[5] = {0, 0, 0, 0, 0}, k1[4], k2[8];
+// ---------------------------------------------------------------------------------------------------------
+// warp-cooperative scalar multiplication (the two 255-bit products s * g_a and r * g1_b of `create_proof`)
+// ---------------------------------------------------------------------------------------------------------
+// A warp instruction costs the multiplier pipe the same 4 cycles whether one lane or 32 are active, so a serial XYZZ
+// ladder on one lane (the first cut: 2.8 ms per proof) wastes the pipe AND the latency.  Here the point lives in shared
+// memory as 48-byte "slots" and every LEVEL of a formula - the field products that do not depend on each other - runs as
+// ONE multiplication issued by the whole warp, each lane on its own pair of operands:
+//   doubling (2008-s-1)  9 products -> 3 levels      addition (add-2008-s) 14 products -> 4 levels
+// Level programs live in constant memory: per lane two operands (a slot, twice / three times a slot, or a difference
+// of two slots), a destination and an optional subtrahend applied to the product.  GLV (k = k1 + k2 lambda, 128-bit halves,
+// table {P, phi P, P + phi P}) halves the doublings; the table stays in XYZZ because a full addition has the same depth as
+// a mixed one once its products spread over the lanes.
+// The formulas have no branches: an addition whose operands are equal (possible for chosen scalars) or whose accumulator
+// is the point at infinity (only for points outside the prime-order subgroup) raises a flag, and the whole product is then
+// redone by one lane with the complete XYZZ routines.
+namespace coop {
+constexpr int ACC = 0;      // slots 0..3: X, Y, ZZ, ZZZ of the accumulator
+constexpr int TMP = 4;      // slots 4..19: temporaries
+constexpr int TAB = 20;     // slots 20..31: table entries P, phi P, P + phi P (4 slots each)
+constexpr int SLOTS = 32;
+constexpr int REL = 64;     // operand indices >= REL address the selected table entry: slot = entry + (index - REL)
+enum Mode : uint8_t { M_S = 0, M_2S = 1, M_3S = 2, M_SUB = 3 };
+struct Opnd { uint8_t i, mode, j; };
+struct MulOp { Opnd a, b; uint8_t dst, post, chk; };   // post: 0xff = none, else result -= slot[post]; chk: 1 = flag if a == 0, 2 = flag if b == 0
+constexpr uint8_t NONE = 0xff;
+constexpr int T(int k) { return TMP + k; }
+// doubling of the accumulator: U = 2Y, V = U^2, W = U V, S = X V, M = 3 X^2, X3 = M^2 - 2S, Y3 = M (S - X3) - W Y, ZZ3 = V ZZ, ZZZ3 = W ZZZ
+__constant__ MulOp DBL1[4] = {{{1, M_2S, 0}, {1, M_2S, 0}, T(0), NONE, 0},     // V
+                              {{0, M_S, 0}, {0, M_S, 0}, T(1), NONE, 0},       // XX
+                              {{1, M_2S, 0}, {1, M_S, 0}, T(2), NONE, 0},      // U Y
+                              {{1, M_2S, 0}, {3, M_S, 0}, T(3), NONE, 0}};     // U ZZZ
+__constant__ MulOp DBL2[5] = {{{0, M_S, 0}, {T(0), M_S, 0}, T(4), NONE, 0},          // S = X V
+                              {{T(1), M_3S, 0}, {T(1), M_3S, 0}, T(5), NONE, 0},     // M^2
+                              {{T(0), M_S, 0}, {T(2), M_S, 0}, T(6), NONE, 0},       // W Y = V (U Y)
+                              {{T(0), M_S, 0}, {2, M_S, 0}, 2, NONE, 0},             // ZZ3
+                              {{T(0), M_S, 0}, {T(3), M_S, 0}, 3, NONE, 0}};         // ZZZ3 = V (U ZZZ)
+// between: X3 = M^2 - 2 S -> slot 0
+__constant__ MulOp DBL3[1] = {{{T(1), M_3S, 0}, {T(4), M_SUB, 0}, 1, T(6), 0}};      // Y3 = M (S - X3) - W Y
+// accumulator + table entry E = (x2, y2, zz2, zzz2) (add-2008-s)
+__constant__ MulOp ADD1[6] = {{{0, M_S, 0}, {REL + 2, M_S, 0}, T(0), NONE, 2},       // U1 = X zz2        (flag: table entry at infinity)
+                              {{REL + 0, M_S, 0}, {2, M_S, 0}, T(1), NONE, 2},       // U2 = x2 ZZ        (flag: accumulator at infinity)
+                              {{1, M_S, 0}, {REL + 3, M_S, 0}, T(2), NONE, 0},       // S1 = Y zzz2
+                              {{REL + 1, M_S, 0}, {3, M_S, 0}, T(3), NONE, 0},       // S2 = y2 ZZZ
+                              {{2, M_S, 0}, {REL + 2, M_S, 0}, T(4), NONE, 0},       // ZZ zz2
+                              {{3, M_S, 0}, {REL + 3, M_S, 0}, T(5), NONE, 0}};      // ZZZ zzz2
+// P = U2 - U1, R = S2 - S1
+__constant__ MulOp ADD2[4] = {{{T(1), M_SUB, T(0)}, {T(1), M_SUB, T(0)}, T(6), NONE, 1},   // PP              (flag: P == 0, equal x)
+                              {{T(3), M_SUB, T(2)}, {T(3), M_SUB, T(2)}, T(7), NONE, 0},   // RR
+                              {{T(1), M_SUB, T(0)}, {T(5), M_S, 0}, T(8), NONE, 0},        // P ZZZ zzz2
+                              {{T(1), M_SUB, T(0)}, {T(2), M_S, 0}, T(9), NONE, 0}};       // S1 P
+__constant__ MulOp ADD3[5] = {{{T(1), M_SUB, T(0)}, {T(6), M_S, 0}, T(10), NONE, 0},       // PPP
+                              {{T(0), M_S, 0}, {T(6), M_S, 0}, T(11), NONE, 0},            // Q = U1 PP
+                              {{T(4), M_S, 0}, {T(6), M_S, 0}, 2, NONE, 0},                // ZZ3
+                              {{T(8), M_S, 0}, {T(6), M_S, 0}, 3, NONE, 0},                // ZZZ3
+                              {{T(9), M_S, 0}, {T(6), M_S, 0}, T(12), NONE, 0}};           // S1 PPP
+// between: X3 = RR - PPP - 2 Q -> slot 0
+__constant__ MulOp ADD4[1] = {{{T(3), M_SUB, T(2)}, {T(11), M_SUB, 0}, 1, T(12), 0}};      // Y3 = R (Q - X3) - S1 PPP
+
+MP_DEV Fq ld(const uint32_t* s, int i) { return Fq::load(s + 12 * i); }
+MP_DEV void st(uint32_t* s, int i, const Fq& v) { v.store(s + 12 * i); }
+MP_DEV Fq fetch(const uint32_t* s, const Opnd& o, int entry) {
+    const int i = o.i >= REL ? entry + (o.i - REL) : o.i;
+    Fq v = ld(s, i);
+    if (o.mode == M_2S) v = v.dbl();
+    else if (o.mode == M_3S) v = v.dbl() + v;
+    else if (o.mode == M_SUB) v = v - ld(s, o.j >= REL ? entry + (o.j - REL) : o.j);
+    return v;
+}
+// one level: lanes < n multiply their operand pairs; all loads happen before any store of the level
+MP_DEV void level(uint32_t* s, const MulOp* ops, int n, int entry, uint32_t lane, uint32_t* flag) {
+    Fq r;
+    uint8_t dst = 0;
+    if ((int)lane < n) {
+        const MulOp op = ops[lane];
+        const Fq a = fetch(s, op.a, entry), b = fetch(s, op.b, entry);
+        if ((op.chk == 1 && a.is_zero()) || (op.chk == 2 && b.is_zero())) *flag = 1;
+        r = a * b;
+        if (op.post != NONE) r = r - ld(s, op.post);
+        dst = op.dst;
+    }
+    __syncwarp();
+    if ((int)lane < n) st(s, dst, r);
+    __syncwarp();
+}
+MP_DEV void dbl(uint32_t* s, uint32_t lane, uint32_t* flag) {
+    level(s, DBL1, 4, 0, lane, flag);
+    level(s, DBL2, 5, 0, lane, flag);
+    if (lane == 0) st(s, 0, ld(s, T(5)) - ld(s, T(4)).dbl());
+    __syncwarp();
+    level(s, DBL3, 1, 0, lane, flag);
+}
+MP_DEV void add(uint32_t* s, int entry, uint32_t lane, uint32_t* flag) {
+    level(s, ADD1, 6, entry, lane, flag);
+    level(s, ADD2, 4, entry, lane, flag);
+    level(s, ADD3, 5, entry, lane, flag);
+    if (lane == 0) st(s, 0, ld(s, T(7)) - ld(s, T(10)) - ld(s, T(11)).dbl());
+    __syncwarp();
+    level(s, ADD4, 1, entry, lane, flag);
+}
+MP_DEV void copy_point(uint32_t* s, int dst, int src, uint32_t lane) {
+    if (lane < 4) st(s, dst + lane, ld(s, src + lane));
+    __syncwarp();
+}
+}  // namespace coop
+
+// k = k2 lambda + k1 by long division (lambda = z^2 - 1, 128 bits; both halves < 2^128 because lambda^2 ~ r)
+MP_COLD void glv_split(const uint32_t* k, uint32_t* k1, uint32_t* k2) {
+    uint32_t rem[5] = {0, 0, 0, 0, 0}, q[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) k2[i] = 0;
+    for (int i = 0; i < 8; i++) q[i] = 0;
     for (int bit = 254; bit >= 0; bit--) {
 #pragma unroll
         for (int i = 4; i > 0; i--) rem[i] = __funnelshift_l(rem[i - 1], rem[i], 1);
@@ -158,24 +258,84 @@ MP_COLD XYZZ<Fq> scalar_mul_glv(const Affine<Fq>& p, const uint32_t* k) {
         if (!borrow) {
 #pragma unroll
             for (int i = 0; i < 5; i++) rem[i] = t[i];
-            k2[bit >> 5] |= 1u << (bit & 31);
+            q[bit >> 5] |= 1u << (bit & 31);
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; i++) k1[i] = rem[i];
-    Affine<Fq> q = {p.x.mul_cold(Fq::from_const(FQ_GLV_BETA)), p.y};
-    XYZZ<Fq> pq = XYZZ<Fq>::from_affine(p).add_mixed_cold(q);
-    XYZZ<Fq> r = XYZZ<Fq>::inf();
-    int bit = 127;
-    while (bit >= 0 && !(((k1[bit >> 5] | k2[bit >> 5]) >> (bit & 31)) & 1)) bit--;
-    for (; bit >= 0; bit--) {
-        r = r.dbl();
-        const uint32_t b1 = (k1[bit >> 5] >> (bit & 31)) & 1, b2 = (k2[bit >> 5] >> (bit & 31)) & 1;
-        if (b1 & b2) r = r.add(pq);
-        else if (b1) r = r.add_mixed_cold(p);
-        else if (b2) r = r.add_mixed_cold(q);
+    for (int i = 0; i < 4; i++) { k1[i] = rem[i]; k2[i] = q[i]; }
+}
+
+// k * P by ONE warp; P given in XYZZ; the result lands in out (XYZZ, 48 words).  s: the warp's coop::SLOTS slots; sc: 16 words
+// of scratch (k1 | k2 | flag).  glv = 0 runs the plain 255-bit ladder (keys with points outside the prime-order subgroup:
+// ark's double-and-add is defined there, phi(P) = lambda P is not).
+MP_DEV void warp_scalar_mul(uint32_t* s, uint32_t* sc, const XYZZ<Fq>& p, const uint32_t* k, int glv, uint32_t lane, uint32_t* out) {
+    using namespace coop;
+    uint32_t* flag = sc + 8;
+    bool kz = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) kz = kz && k[i] == 0;
+    if (p.is_inf() || kz) {
+        if (lane == 0) XYZZ<Fq>::inf().store(out);
+        __syncwarp();
+        return;
     }
-    return r;
+    if (lane == 0) {
+        *flag = 0;
+        if (glv) glv_split(k, sc, sc + 4);
+        else
+            for (int i = 0; i < 8; i++) sc[i] = k[i];
+        st(s, TAB + 0, p.X); st(s, TAB + 1, p.Y); st(s, TAB + 2, p.ZZ); st(s, TAB + 3, p.ZZZ);
+        if (glv) {  // phi(P) = (beta x, y): scale X
+            st(s, TAB + 4, p.X.mul_cold(Fq::from_const(FQ_GLV_BETA))); st(s, TAB + 5, p.Y); st(s, TAB + 6, p.ZZ); st(s, TAB + 7, p.ZZZ);
+        }
+    }
+    __syncwarp();
+    int bit;
+    if (glv) {
+        copy_point(s, ACC, TAB, lane);
+        add(s, TAB + 4, lane, flag);           // P + phi P (never degenerate: phi P = lambda P, lambda != +-1)
+        copy_point(s, TAB + 8, ACC, lane);
+        const uint32_t* k1 = sc;
+        const uint32_t* k2 = sc + 4;
+        bit = 127;
+        while (bit >= 0 && !(((k1[bit >> 5] | k2[bit >> 5]) >> (bit & 31)) & 1)) bit--;
+        bool first = true;
+        for (; bit >= 0; bit--) {
+            const uint32_t sel = ((k1[bit >> 5] >> (bit & 31)) & 1) | (((k2[bit >> 5] >> (bit & 31)) & 1) << 1);
+            if (!first) dbl(s, lane, flag);
+            if (sel) {
+                const int entry = TAB + 4 * (int)(sel - 1);   // 1: P, 2: phi P, 3: P + phi P
+                if (first) copy_point(s, ACC, entry, lane);
+                else add(s, entry, lane, flag);
+                first = false;
+            }
+        }
+    } else {
+        bit = 254;
+        while (bit >= 0 && !((sc[bit >> 5] >> (bit & 31)) & 1)) bit--;
+        copy_point(s, ACC, TAB, lane);
+        for (bit--; bit >= 0; bit--) {
+            dbl(s, lane, flag);
+            if ((sc[bit >> 5] >> (bit & 31)) & 1) add(s, TAB, lane, flag);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        XYZZ<Fq> r;
+        if (*flag) {  // a degenerate addition was met: complete formulas, one lane
+            r = XYZZ<Fq>::inf();
+            int b = 254;
+            while (b >= 0 && !((k[b >> 5] >> (b & 31)) & 1)) b--;
+            for (; b >= 0; b--) {
+                r = r.dbl();
+                if ((k[b >> 5] >> (b & 31)) & 1) r = r.add(p);
+            }
+        } else {
+            r = {ld(s, 0), ld(s, 1), ld(s, 2), ld(s, 3)};
+        }
+        r.store(out);
+    }
+    __syncwarp();
 }
 
 MP_DEV void write_fq_le(uint8_t* out, const Fq& canon) {
@@ -212,31 +372,34 @@ MP_COLD void compress_g2(uint8_t* out, const Affine<Fq2>& p) {
     if (larger) out[95] |= 0x80;
 }
 
-// One block per proof, three warps with one active lane each:
-//   warp 0: g_a -> affine, s*g_a        warp 1: g1_b -> affine, r*g1_b        warp 2: g2_b -> affine, L + H
-// then thread 0 assembles g_c and writes the 192 proof bytes.
+// One block per proof, five warps:
+//   warp 0: s * g_a          warp 1: r * g1_b          (warp-cooperative ladders)
+//   warp 2: L + H            warp 3: g_a -> affine -> bytes     warp 4: g2_b -> affine -> bytes     (one lane each)
+// then thread 0 assembles g_c = s g_a + r g1_b + L + H (the -rs delta_1 term rides inside the L MSM) and writes its bytes.
 // res_g1: [4][batch] XYZZ (A, B1, L, H); res_g2: [batch] XYZZ.
-__global__ void __launch_bounds__(96) k_prove_finish(const XYZZ<Fq>* __restrict__ res_g1, const XYZZ<Fq2>* __restrict__ res_g2,
-                                                    const uint32_t* __restrict__ rs, uint32_t batch, uint8_t* proofs) {
+constexpr int FINISH_THREADS = 160;
+__global__ void __launch_bounds__(FINISH_THREADS) k_prove_finish(const XYZZ<Fq>* __restrict__ res_g1, const XYZZ<Fq2>* __restrict__ res_g2,
+                                                                const uint32_t* __restrict__ rs, uint32_t batch, int glv, uint8_t* proofs) {
+    __shared__ __align__(16) uint32_t slots[2][coop::SLOTS * 12];
+    __shared__ __align__(16) uint32_t scratch[2][16];
     __shared__ __align__(16) uint32_t sh_sa[48], sh_rb[48], sh_lh[48];
     const uint32_t b = blockIdx.x;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* out = proofs + (size_t)b * MP_PROOF_BYTES;
     const uint32_t* r = rs + (size_t)b * 16;
     const uint32_t* s = r + 8;
-    if (lane == 0) {
-        if (warp == 0) {
-            Affine<Fq> a = XYZZ<Fq>::load(res_g1 + b).to_affine();
-            compress_g1(out, a);
-            scalar_mul_glv(a, s).store(sh_sa);
-        } else if (warp == 1) {
-            Affine<Fq> b1 = XYZZ<Fq>::load(res_g1 + (size_t)batch + b).to_affine();
-            scalar_mul_glv(b1, r).store(sh_rb);
-        } else {
-            Affine<Fq2> b2 = XYZZ<Fq2>::load(res_g2 + b).to_affine();
-            compress_g2(out + 48, b2);
+    if (warp == 0) {
+        warp_scalar_mul(slots[0], scratch[0], XYZZ<Fq>::load(res_g1 + b), s, glv, lane, sh_sa);
+    } else if (warp == 1) {
+        warp_scalar_mul(slots[1], scratch[1], XYZZ<Fq>::load(res_g1 + (size_t)batch + b), r, glv, lane, sh_rb);
+    } else if (lane == 0) {
+        if (warp == 2) {
             XYZZ<Fq> lh = XYZZ<Fq>::load(res_g1 + (size_t)2 * batch + b).add(XYZZ<Fq>::load(res_g1 + (size_t)3 * batch + b));
             lh.store(sh_lh);
+        } else if (warp == 3) {
+            compress_g1(out, XYZZ<Fq>::load(res_g1 + b).to_affine());
+        } else {
+            compress_g2(out + 48, XYZZ<Fq2>::load(res_g2 + b).to_affine());
         }
     }
     __syncthreads();
@@ -244,6 +407,21 @@ __global__ void __launch_bounds__(96) k_prove_finish(const XYZZ<Fq>* __restrict_
         XYZZ<Fq> c = XYZZ<Fq>::load(sh_sa).add(XYZZ<Fq>::load(sh_rb)).add(XYZZ<Fq>::load(sh_lh));
         compress_g1(out + 144, c.to_affine());
     }
+}
+
+// [r] P == infinity for every point of a query (prime-order subgroup membership; enables the GLV ladder of the finishing kernel)
+template <class F>
+__global__ void __launch_bounds__(64) k_subgroup_check(const uint32_t* __restrict__ pts, size_t n, uint32_t* outside) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p = Affine<F>::load(pts + i * Affine<F>::WORDS);
+    if (p.is_inf()) return;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int bit = 254; bit >= 0; bit--) {
+        acc = acc.dbl();
+        if ((FR_MOD[bit >> 5] >> (bit & 31)) & 1) acc = acc.add_mixed_cold(p);
+    }
+    if (!acc.is_inf()) atomicAdd(outside, 1u);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -265,6 +443,21 @@ static int assemble_bases(DevBuf& out, size_t stride, size_t front_pad, const ui
     MP_CUDA_TRY(cudaStreamSynchronize(st));
     if (G2) MP_TRY(points_from_ark_g2(out.p, out.p, stride, st));
     else MP_TRY(points_from_ark_g1(out.p, out.p, stride, st));
+    return MP_OK;
+}
+
+// The GLV ladder of the finishing kernel is only valid on the prime-order subgroup; the key is loaded like the reference's
+// `deserialize_unchecked`, so membership of the points behind g_a and g1_b is established here, once per context.
+static int check_subgroup_g1(mp_ctx* c, const DevBuf& bases, size_t n, cudaStream_t st) {
+    DevBuf cnt;
+    MP_TRY(cnt.alloc(4));
+    MP_CUDA_TRY(cudaMemsetAsync(cnt.p, 0, 4, st));
+    k_subgroup_check<Fq><<<div_up(n, 64), 64, 0, st>>>(bases.as<uint32_t>(), n, cnt.as<uint32_t>());
+    MP_KERNEL_CHECK();
+    uint32_t outside = 0;
+    MP_CUDA_TRY(cudaMemcpyAsync(&outside, cnt.p, 4, cudaMemcpyDeviceToHost, st));
+    MP_CUDA_TRY(cudaStreamSynchronize(st));
+    if (outside) c->glv = false;
     return MP_OK;
 }
 
@@ -311,9 +504,11 @@ static int ctx_create_impl(const mp_pk_view* pk, const mp_r1cs_view* r1cs, int d
         DevBuf bases;
         const uint8_t* ex_a[N_EXTRA] = {pk->delta_g1, nullptr, nullptr, pk->alpha_g1};
         MP_TRY(assemble_bases<false>(bases, c->zlen, 0, pk->a_query, c->n, c->n, ex_a, st));
+        MP_TRY(check_subgroup_g1(c, bases, c->zlen, st));
         MP_TRY(build_table<false>(c, c->gz, c->tab_a, bases, c->valid_a, false, st));
         const uint8_t* ex_b1[N_EXTRA] = {nullptr, pk->delta_g1, nullptr, pk->beta_g1};
         MP_TRY(assemble_bases<false>(bases, c->zlen, 0, pk->b_g1_query, c->n, c->n, ex_b1, st));
+        MP_TRY(check_subgroup_g1(c, bases, c->zlen, st));
         MP_TRY(build_table<false>(c, c->gz, c->tab_b1, bases, c->valid_b, false, st));
         const uint8_t* ex_l[N_EXTRA] = {nullptr, nullptr, pk->delta_g1, nullptr};
         MP_TRY(assemble_bases<false>(bases, c->zlen, c->p, pk->l_query, c->w, c->n, ex_l, st));
@@ -326,6 +521,8 @@ static int ctx_create_impl(const mp_pk_view* pk, const mp_r1cs_view* r1cs, int d
         MP_TRY(build_table<true>(c, c->gz, c->tab_b2, bases, c->valid_b, true, st));  // B list keeps a scalar if either B1 or B2 base is finite
     }
     MP_CUDA_TRY(cudaDeviceSynchronize());
+    if (const char* e = getenv("MP_NO_GLV"))
+        if (e[0] && e[0] != '0') c->glv = false;  // test hook: plain 255-bit ladder
     return MP_OK;
 }
 
@@ -480,8 +677,8 @@ static int batch_enqueue(mp_batch* b) {
     MP_TRY(msm_reduce_tail_g1(g1, 4, cnt, ba1, st));
     if (b->overlap) MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_g2, 0));
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_FINISH], st));
-    k_prove_finish<<<(unsigned)cnt, 96, 0, st>>>(b->res_g1.as<XYZZ<Fq>>(), b->res_g2.as<XYZZ<Fq2>>(), b->rs.as<uint32_t>(),
-                                                 (uint32_t)cnt, b->proofs.as<uint8_t>());
+    k_prove_finish<<<(unsigned)cnt, FINISH_THREADS, 0, st>>>(b->res_g1.as<XYZZ<Fq>>(), b->res_g2.as<XYZZ<Fq2>>(), b->rs.as<uint32_t>(),
+                                                             (uint32_t)cnt, c->glv ? 1 : 0, b->proofs.as<uint8_t>());
     MP_KERNEL_CHECK();
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_COUNT], st));
     b->launches = kernel_launch_counter() - launches0;

@@ -392,6 +392,68 @@ def test_unsatisfied_assignment_matches_oracle(native):
     ctx.close()
 
 
+def test_key_with_points_outside_the_subgroup_and_plain_ladder(native, monkeypatch):
+    """The key is loaded like the reference's `deserialize_unchecked`: a_query / b_g1_query points that lie on the curve but
+    outside the prime-order subgroup must still give ark's double-and-add result (the finishing kernel then drops its GLV
+    ladder, which is only valid on the subgroup).  Also the plain ladder forced on a well-formed key."""
+    from manta_rs_b200 import groth16 as g16
+    from oracle.pyref.curves import Group
+    G1 = Group(C, 1)
+    cs = wl.make_r1cs(3, 50, dist="R")
+    pk, trap = oracle_keygen(cs, wl.sample_trapdoor(31))
+    rng = random.Random(31)
+    outside = []
+    while len(outside) < 2:
+        x = rng.randrange(C.q)
+        try:
+            P = G1.decompress(x.to_bytes(48, "little"))
+        except AssertionError:
+            continue
+        if G1.mul(P, C.r) is not None:
+            outside.append(G1.serialize_uncompressed(P))
+    pos_a = 96 + 192 * 3 + 8 + 96 * cs.p + 96 * 2 + 8
+    pos_b1 = pos_a + 96 * cs.n + 8
+    bad = bytearray(pk)
+    bad[pos_a + 96 * 2:pos_a + 96 * 3] = outside[0]
+    bad[pos_b1 + 96 * 3:pos_b1 + 96 * 4] = outside[1]
+    bad = bytes(bad)
+    zs = [wl.make_assignment(cs, s) for s in (1, 2)]
+    rs, ss = [rng.randrange(C.r) for _ in zs], [rng.randrange(C.r) for _ in zs]
+    ctx = g16.ProvingContext.decode(bad)
+    op = cref.OracleProver(bad, cs.p, cs.w, cs.a, cs.b, cs.c)
+    for z, r, s in zip(zs, rs, ss):
+        pr = g16.Groth16.prove_with_randomness(ctx, g16.R1CS.from_workload(cs, z), r, s)
+        assert pr.to_bytes() == op.prove(z, r, s, threads=4)
+    ctx.close()
+    monkeypatch.setenv("MP_NO_GLV", "1")
+    ctx = g16.ProvingContext.decode(pk)
+    for z, r, s in zip(zs, rs, ss):
+        pr = g16.Groth16.prove_with_randomness(ctx, g16.R1CS.from_workload(cs, z), r, s)
+        assert pr.to_bytes() == trapdoor_proof_bytes(cs, trap, z, r, s)
+    ctx.close()
+
+
+def test_finish_ladder_special_scalars(native):
+    """r, s that stress the warp-cooperative ladders of the finishing kernel: 0, 1, 2, lambda (k1 = 0), lambda + 1, r - 1, powers
+    of two, and a scalar whose GLV halves make the accumulator meet a table entry (equal operands -> complete-formula fallback)."""
+    from manta_rs_b200 import groth16 as g16
+    lam = 0xAC45A4010001A40200000000FFFFFFFF
+    cs = wl.make_r1cs(2, 20)
+    pk, trap = oracle_keygen(cs, wl.sample_trapdoor(32))
+    ctx = g16.ProvingContext.decode(pk)
+    z = wl.make_assignment(cs, 3)
+    zsq_half = (lam + 1) // 2                      # k1 prefix = z^2 / 2 followed by bits (1, 1) with k2 = 1: acc = (1 + lambda) P meets P + phi P
+    tricky = (2 * zsq_half + 1) + 1 * lam
+    vals = [0, 1, 2, 3, lam, lam + 1, lam - 1, 2 * lam, C.r - 1, C.r - 2, 1 << 127, 1 << 128, (1 << 254), tricky % C.r, (lam * lam) % C.r]
+    comp = g16.R1CS.from_workload(cs, z)
+    rs = vals
+    ss = vals[1:] + vals[:1]
+    proofs = g16.Groth16.prove_many_with_randomness(ctx, [comp] * len(vals), rs, ss)
+    for r, s, pr in zip(rs, ss, proofs):
+        assert pr.to_bytes() == trapdoor_proof_bytes(cs, trap, z, r, s), (r, s)
+    ctx.close()
+
+
 def test_mpc_style_key_with_h_len_m(native):
     """Production keys come from the MPC and carry m (not m - 1) h_query points (mpc.rs:371-377)."""
     cs = wl.make_r1cs(3, 29)
