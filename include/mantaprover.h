@@ -166,6 +166,24 @@ MP_API int mp_witness_map(mp_ctx* ctx, const uint64_t* z, uint64_t* out_h);
 MP_API int mp_fixed_base_g1(int device, const uint64_t* scalars, size_t n, uint8_t* out /* n x 96 */);
 MP_API int mp_fixed_base_g2(int device, const uint64_t* scalars, size_t n, uint8_t* out /* n x 192 */);
 
+/* Whole keys on the device.  Both write the `ProvingContext` encoding (groth16.rs:290-303) into out_pk; with out_pk == NULL they
+ * only report the size in *out_len.
+ *   mp_keygen: `Groth16::compile` (groth16.rs:570-586 -> ark `generate_parameters`) for a known trapdoor
+ *     (tau, alpha, beta, gamma, delta; 5 x 4 limbs canonical, all non-zero) and the standard generators: Lagrange basis at tau,
+ *     the QAP polynomials u_i, v_i, w_i of every variable (column sums of A, B, C), then 5n + m fixed-base multiplications.
+ *     h_len = 0 selects ark's m - 1 h_query points, h_len = m the MPC form.
+ *   mp_mpc_initialize: phase-2 `initialize` of the trusted setup (manta-trusted-setup/src/groth16/mpc.rs:355-431) from the phase-1
+ *     powers tau^i G1 (>= 2m), tau^i G2, alpha tau^i G1, beta tau^i G1 (m each) and beta G2: h_query[i] = tau^(i+m) G - tau^i G,
+ *     four group-valued inverse FFTs of size m, the sparse accumulation of :245-312, gamma = delta = 1.
+ *   mp_group_ntt: the group-valued radix-2 transform alone (ark-poly `domain.fft / ifft` over curve points), in place on
+ *     2^log_n uncompressed points. */
+MP_API int mp_keygen(int device, const mp_r1cs_view* r1cs, const uint64_t* trapdoor /* 5 x 4 */, uint64_t h_len, uint8_t* out_pk,
+                     size_t out_cap, size_t* out_len);
+MP_API int mp_mpc_initialize(int device, const mp_r1cs_view* r1cs, const uint8_t* tau_powers_g1, size_t n_tau_g1,
+                             const uint8_t* tau_powers_g2, const uint8_t* alpha_tau_powers_g1, const uint8_t* beta_tau_powers_g1,
+                             const uint8_t* beta_g2, uint8_t* out_pk, size_t out_cap, size_t* out_len);
+MP_API int mp_group_ntt(int device, int group, uint8_t* points, unsigned log_n, int inverse);
+
 /* ---- witness-side Fr work -------------------------------------------------------------------
  * Batched Poseidon permutation over BLS12-381 Fr: `Permutation::permute` of manta-pay/src/crypto/poseidon/mod.rs:385-421,
  * 515-518 applied in place to `count` independent states of `width` elements (canonical, 4 limbs each).  round_keys:

@@ -75,6 +75,9 @@ SYMBOLS = {
     "mp_witness_map": (_I, [_V, _V, _V]),
     "mp_fixed_base_g1": (_I, [_I, _V, _SZ, _V]),
     "mp_fixed_base_g2": (_I, [_I, _V, _SZ, _V]),
+    "mp_keygen": (_I, [_I, _V, _V, ctypes.c_uint64, _V, _SZ, _V]),
+    "mp_mpc_initialize": (_I, [_I, _V, _V, _SZ, _V, _V, _V, _V, _V, _SZ, _V]),
+    "mp_group_ntt": (_I, [_I, _I, _V, _U, _I]),
     "mp_poseidon_permute": (_I, [_I, _I, _I, _I, _V, _V, _V, _SZ, _V]),
     "mp_debug_field_op": (_I, [_I, _I, _I, _V, _V, _V, _SZ]),
     "mp_debug_group_op": (_I, [_I, _I, _I, _V, _V, _V, _V, _SZ]),

@@ -131,6 +131,10 @@ int msm_validity_g2(const void* bases, uint32_t n, uint32_t* bitmap, bool accumu
 int msm_build_table_g1(const MsmGeom& g, const void* bases, uint32_t n, void* out, cudaStream_t st);
 int msm_build_table_g2(const MsmGeom& g, const void* bases, uint32_t n, void* out, cudaStream_t st);
 
+// out[i] = scalars[i] * G (standard generator), device-resident: canonical Fr in, Affine<F> Montgomery out
+int msm_fixed_base_dev_g1(const void* d_scalars, size_t n, void* d_out, cudaStream_t st);
+int msm_fixed_base_dev_g2(const void* d_scalars, size_t n, void* d_out, cudaStream_t st);
+
 // Horner over window groups: out = sum_g 2^(c*g) * result[g]  (one thread per MSM; only when groups > 1)
 int msm_horner_g1(const MsmGeom& g, const void* group_results, void* out_xyzz, size_t count, cudaStream_t st);
 int msm_horner_g2(const MsmGeom& g, const void* group_results, void* out_xyzz, size_t count, cudaStream_t st);

@@ -20,6 +20,7 @@ namespace mp {
 constexpr int NTT_TILE = 2048;      // Fr elements per block tile (64 KiB)
 constexpr int NTT_THREADS = 256;
 constexpr unsigned NTT_MAX_SUB = 10;  // largest in-SMEM sub-transform (2^10 points)
+constexpr unsigned NTT_MAX_LOG = 26;  // two passes up to 2^20, three up to 2^26 (kzg.rs:43-44 powers; SURVEY.md 5 size axis)
 
 struct NttArgs {
     const uint32_t* in;
@@ -30,6 +31,10 @@ struct NttArgs {
     const uint32_t* post_c; // nullable, 1 entry
     unsigned log_n, l1, l2; // n = 2^log_n = 2^l1 * 2^l2
     size_t in_stride, out_stride;  // elements between consecutive vectors
+    // Nested use (transforms above 2^20 points): this launch runs the 2^outer_l1 row transforms of an outer four-step split.
+    // Vector v = V * 2^outer_l1 + k1 is row k1 of outer transform V; its twiddles are w_N^(k << outer_l1) (tw belongs to the
+    // OUTER domain of N = n * 2^outer_l1 points) and its output k lands at index k1 + (k << outer_l1) of outer vector V.
+    unsigned outer_l1;
 };
 
 MP_DEV unsigned brev_bits(unsigned p, unsigned lg) { return lg ? (__brev(p) >> (32 - lg)) : 0u; }
@@ -131,7 +136,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_cols(NttArgs a) {
     uint32_t* tile = smem;
     uint32_t* tws = smem + (size_t)NTT_TILE * 8;
     const uint32_t* in = a.in + v * a.in_stride * 8;
-    for (unsigned e = threadIdx.x; e < (n1 >> 1); e += NTT_THREADS) Fr::load(a.tw + ((size_t)e << a.l2) * 8).store(tws + (size_t)e * 8);
+    for (unsigned e = threadIdx.x; e < (n1 >> 1); e += NTT_THREADS) Fr::load(a.tw + (((size_t)e << a.l2) << a.outer_l1) * 8).store(tws + (size_t)e * 8);
     __shared__ __align__(8) uint64_t bar;
     if (!a.pre) {
         // tile[j][c] <- in[j * n2 + c0 + c]: n1 rows of C * 32 bytes, one bulk copy each
@@ -160,7 +165,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_cols(NttArgs a) {
         unsigned k1 = brev_bits(p, a.l1);
         Fr x = Fr::load(tile + (size_t)idx * 8);
         unsigned te = (k1 * (c0 + c)) & nmask;
-        if (te) x = x * Fr::load(a.tw + (size_t)te * 8);
+        if (te) x = x * Fr::load(a.tw + ((size_t)te << a.outer_l1) * 8);
         x.store(out + ((size_t)k1 * n2 + c0 + c) * 8);
     }
 }
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_rows(NttArgs a) {
     uint32_t* tile = smem;
     uint32_t* tws = smem + (size_t)(NTT_TILE + 64) * 8;
     const uint32_t* in = a.in + v * a.in_stride * 8;
-    for (unsigned e = threadIdx.x; e < (n2 >> 1); e += NTT_THREADS) Fr::load(a.tw + ((size_t)e << a.l1) * 8).store(tws + (size_t)e * 8);
+    for (unsigned e = threadIdx.x; e < (n2 >> 1); e += NTT_THREADS) Fr::load(a.tw + (((size_t)e << a.l1) << a.outer_l1) * 8).store(tws + (size_t)e * 8);
     __shared__ __align__(8) uint64_t bar;
     if (!(a.l1 == 0 && a.pre)) {
         // tile row c (padded stride rs) <- the n2 contiguous elements of global row r0 + c: one bulk copy per row
@@ -198,13 +203,14 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_rows(NttArgs a) {
     }
     __syncthreads();
     smem_dif(tile, tws, a.l2, lR, 1, rs, false);
-    uint32_t* out = a.out + v * a.out_stride * 8;
+    const size_t k1o = v & (((size_t)1 << a.outer_l1) - 1);   // row of the outer split (0 when not nested)
+    uint32_t* out = a.out + (v >> a.outer_l1) * a.out_stride * 8;
     Fr pc;
     if (a.post_c) pc = Fr::load(a.post_c);
     for (unsigned idx = threadIdx.x; idx < n2 * R; idx += NTT_THREADS) {
         unsigned c = idx & (R - 1), p = idx >> lR;
         unsigned k2 = brev_bits(p, a.l2);
-        size_t k = (size_t)(r0 + c) + ((size_t)k2 << a.l1);
+        const size_t k = k1o + (((size_t)(r0 + c) + ((size_t)k2 << a.l1)) << a.outer_l1);
         Fr x = Fr::load(tile + (size_t)(c * rs + p) * 8);
         if (a.post) x = x * Fr::load(a.post + k * 8);
         else if (a.post_c) x = x * pc;
@@ -214,33 +220,32 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_rows(NttArgs a) {
 
 static size_t ntt_smem_bytes(unsigned lsub) { return ((size_t)NTT_TILE + 64 + (size_t)(1u << lsub) / 2) * 32; }
 
-int ntt_run_strided(const NttDomain& d, bool inverse, const void* in, void* out, void* tmp, size_t count, size_t in_stride,
-                    size_t out_stride, const void* pre, const void* post, const void* post_c, cudaStream_t st) {
-    if (count == 0) return MP_OK;
-    MP_CUDA_TRY(cudaFuncSetAttribute(k_ntt_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_MAX_SUB)));
-    MP_CUDA_TRY(cudaFuncSetAttribute(k_ntt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_MAX_SUB)));
-    NttArgs a{};
-    a.tw = (const uint32_t*)(inverse ? d.tw_inv.p : d.tw_fwd.p);
-    a.pre = (const uint32_t*)pre;
-    a.post = (const uint32_t*)post;
-    a.post_c = (const uint32_t*)post_c;
-    a.log_n = d.log_n;
-    if (d.log_n <= NTT_MAX_SUB) {
+// The two shared-memory passes of one (possibly nested) transform of 2^log_n points per vector.
+static int ntt_two_pass(NttArgs a, unsigned log_n, const void* in, void* out, void* tmp, size_t count, size_t in_stride, size_t out_stride,
+                        cudaStream_t st) {
+    a.log_n = log_n;
+    if (log_n <= NTT_MAX_SUB) {
         a.l1 = 0;
-        a.l2 = d.log_n;
+        a.l2 = log_n;
         a.in = (const uint32_t*)in;
         a.out = (uint32_t*)out;
         a.in_stride = in_stride;
         a.out_stride = out_stride;
-        k_ntt_rows<<<dim3(1, (unsigned)count), NTT_THREADS, ntt_smem_bytes(a.l2), st>>>(a);
-        MP_KERNEL_CHECK();
+        for (size_t v0 = 0; v0 < count; v0 += 65535) {   // gridDim.y limit
+            NttArgs b = a;
+            b.in += v0 * in_stride * 8;
+            if (a.outer_l1 == 0) b.out += v0 * out_stride * 8;
+            else if (v0) return MP_ERR_UNSUPPORTED;
+            k_ntt_rows<<<dim3(1, (unsigned)std::min<size_t>(65535, count - v0)), NTT_THREADS, ntt_smem_bytes(a.l2), st>>>(b);
+            MP_KERNEL_CHECK();
+        }
         return MP_OK;
     }
-    a.l1 = (d.log_n + 1) / 2;
-    a.l2 = d.log_n - a.l1;
-    if (a.l1 > NTT_MAX_SUB) { set_error_detail("ntt: log_n = %u exceeds %u", d.log_n, 2 * NTT_MAX_SUB); return MP_ERR_UNSUPPORTED; }
+    a.l1 = (log_n + 1) / 2;
+    a.l2 = log_n - a.l1;
     const unsigned n1 = 1u << a.l1, n2 = 1u << a.l2;
     const unsigned C = std::min<unsigned>(NTT_TILE >> a.l1, n2), R = std::min<unsigned>(NTT_TILE >> a.l2, n1);
+    if (count > 65535) return MP_ERR_UNSUPPORTED;
     NttArgs p1 = a;
     p1.in = (const uint32_t*)in;
     p1.out = (uint32_t*)tmp;
@@ -259,9 +264,43 @@ int ntt_run_strided(const NttDomain& d, bool inverse, const void* in, void* out,
     return MP_OK;
 }
 
+// Up to 2^20 points: two passes.  Above (<= 2^NTT_MAX_LOG): one more column pass in front - an outer four-step split
+// N = 2^o x 2^20 whose 2^o row transforms of 2^20 points are the nested two-pass launches; needs the second scratch `tmp2`.
+int ntt_run_strided(const NttDomain& d, bool inverse, const void* in, void* out, void* tmp, size_t count, size_t in_stride,
+                    size_t out_stride, const void* pre, const void* post, const void* post_c, cudaStream_t st, void* tmp2) {
+    if (count == 0) return MP_OK;
+    MP_CUDA_TRY(cudaFuncSetAttribute(k_ntt_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_MAX_SUB)));
+    MP_CUDA_TRY(cudaFuncSetAttribute(k_ntt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_MAX_SUB)));
+    NttArgs a{};
+    a.tw = (const uint32_t*)(inverse ? d.tw_inv.p : d.tw_fwd.p);
+    a.pre = (const uint32_t*)pre;
+    a.post = (const uint32_t*)post;
+    a.post_c = (const uint32_t*)post_c;
+    if (d.log_n <= 2 * NTT_MAX_SUB) return ntt_two_pass(a, d.log_n, in, out, tmp, count, in_stride, out_stride, st);
+    if (!tmp2 || in_stride != d.n) { set_error_detail("ntt: 2^%u points need the second scratch buffer and contiguous vectors", d.log_n); return MP_ERR_UNSUPPORTED; }
+    const unsigned o = d.log_n - 2 * NTT_MAX_SUB, li = 2 * NTT_MAX_SUB;   // outer rows 2^o (o <= NTT_MAX_SUB), inner 2^20
+    if (count << o > 65535) return MP_ERR_UNSUPPORTED;
+    // outer pass 1: for every column i2 < 2^li, the 2^o-point transform over stride 2^li, times w_N^(i2 k1); rows k1 stay contiguous
+    NttArgs p1 = a;
+    p1.log_n = d.log_n;
+    p1.l1 = o;
+    p1.l2 = li;
+    p1.in = (const uint32_t*)in;
+    p1.out = (uint32_t*)tmp;
+    p1.in_stride = p1.out_stride = in_stride;
+    const unsigned C = NTT_TILE >> o;
+    k_ntt_cols<<<dim3((1u << li) / C, (unsigned)count), NTT_THREADS, ntt_smem_bytes(o), st>>>(p1);
+    MP_KERNEL_CHECK();
+    // the 2^o rows of every vector: 2^li-point transforms with the outer domain's twiddles, scattered to k1 + (k << o)
+    NttArgs in2 = a;
+    in2.pre = nullptr;
+    in2.outer_l1 = o;
+    return ntt_two_pass(in2, li, tmp, out, tmp2, count << o, (size_t)1 << li, out_stride, st);
+}
+
 int ntt_run(const NttDomain& d, bool inverse, const void* in, void* out, void* tmp, size_t count, const void* pre,
             const void* post, const void* post_c, cudaStream_t st) {
-    return ntt_run_strided(d, inverse, in, out, tmp, count, d.n, d.n, pre, post, post_c, st);
+    return ntt_run_strided(d, inverse, in, out, tmp, count, d.n, d.n, pre, post, post_c, st, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -307,7 +346,7 @@ __global__ void k_ntt_tables(unsigned log_n, uint32_t* tw_fwd, uint32_t* tw_inv,
 }
 
 int ntt_domain_create(NttDomain& d, unsigned log_n, cudaStream_t st) {
-    if (log_n > 2 * NTT_MAX_SUB) { set_error_detail("ntt: log_n = %u exceeds %u", log_n, 2 * NTT_MAX_SUB); return MP_ERR_UNSUPPORTED; }
+    if (log_n > NTT_MAX_LOG) { set_error_detail("ntt: log_n = %u exceeds %u", log_n, NTT_MAX_LOG); return MP_ERR_UNSUPPORTED; }
     d.log_n = log_n;
     d.n = (size_t)1 << log_n;
     size_t bytes = d.n * 32;
@@ -448,7 +487,7 @@ int witness_map_run(const NttDomain& d, void* abc, void* s1, void* s2, size_t co
     k_quotient_numerator<<<dim3(div_up(m, 256), (unsigned)count), 256, 0, st>>>((const uint32_t*)abc, (uint32_t*)s1, m, count);
     MP_KERNEL_CHECK();
     // coset_ifft with 1/(m Z(g)) g^-i and the Montgomery -> canonical conversion folded into the store
-    MP_TRY(ntt_run_strided(d, true, s1, out_h, s2, count, m, h_stride, nullptr, d.post_h.p, nullptr, st));
+    MP_TRY(ntt_run_strided(d, true, s1, out_h, s2, count, m, h_stride, nullptr, d.post_h.p, nullptr, st, nullptr));
     return MP_OK;
 }
 
@@ -462,10 +501,11 @@ extern "C" int mp_ntt(int device, uint64_t* data, unsigned log_n, int inverse, i
     NttDomain d;
     MP_TRY(ntt_domain_create(d, log_n, 0));
     size_t bytes = d.n * 32;
-    DevBuf a, b, c;
+    DevBuf a, b, c, c2;
     MP_TRY(a.alloc(bytes));
     MP_TRY(b.alloc(bytes));
     MP_TRY(c.alloc(bytes));
+    if (log_n > 2 * NTT_MAX_SUB) MP_TRY(c2.alloc(bytes));
     MP_CUDA_TRY(cudaMemcpy(a.p, data, bytes, cudaMemcpyHostToDevice));
     MP_TRY(fr_to_mont(a.p, a.p, d.n, 0));
     EventTimer timer;
@@ -473,7 +513,7 @@ extern "C" int mp_ntt(int device, uint64_t* data, unsigned log_n, int inverse, i
     const void* pre = (!inverse && coset) ? d.pre_coset.p : nullptr;
     const void* post = (inverse && coset) ? d.post_coset_inv.p : nullptr;
     const void* post_c = (inverse && !coset) ? d.post_inv.p : nullptr;
-    MP_TRY(ntt_run(d, inverse != 0, a.p, b.p, c.p, 1, pre, post, post_c, 0));
+    MP_TRY(ntt_run_strided(d, inverse != 0, a.p, b.p, c.p, 1, d.n, d.n, pre, post, post_c, 0, c2.p));
     MP_TRY(timer.stop(0));
     MP_TRY(fr_from_mont(b.p, b.p, d.n, 0));
     MP_CUDA_TRY(cudaMemcpy(data, b.p, bytes, cudaMemcpyDeviceToHost));

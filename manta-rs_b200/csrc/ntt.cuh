@@ -25,6 +25,11 @@ int ntt_domain_create(NttDomain& d, unsigned log_n, cudaStream_t st);
 int ntt_run(const NttDomain& d, bool inverse, const void* in, void* out, void* tmp, size_t count,
             const void* pre_table, const void* post_table, const void* post_const, cudaStream_t st);
 
+// General form: vectors `in_stride` / `out_stride` elements apart.  Transforms above 2^20 points take a third pass and need
+// `tmp2`, a second scratch buffer of count * n elements (nullptr otherwise).
+int ntt_run_strided(const NttDomain& d, bool inverse, const void* in, void* out, void* tmp, size_t count, size_t in_stride,
+                    size_t out_stride, const void* pre_table, const void* post_table, const void* post_const, cudaStream_t st, void* tmp2);
+
 // CSR matrices on the device, coefficients in Montgomery form.
 struct R1csDev {
     uint64_t p = 0, w = 0, K = 0;

@@ -493,6 +493,7 @@ static int ctx_create_impl(const mp_pk_view* pk, const mp_r1cs_view* r1cs, int d
     c->log_m = 0;
     while (((uint64_t)1 << c->log_m) < c->K + c->p) c->log_m++;
     c->m = (uint64_t)1 << c->log_m;
+    if (c->log_m > 20) { set_error_detail("prover: domain 2^%u exceeds 2^20 (the stand-alone transform mp_ntt goes to 2^26)", c->log_m); return MP_ERR_UNSUPPORTED; }
     if (pk->h_len + 1 < c->m) { set_error_detail("h_query shorter than m - 1"); return MP_ERR_INVALID_ARG; }
     c->zlen = (uint32_t)c->n + N_EXTRA;
     cudaStream_t st = 0;

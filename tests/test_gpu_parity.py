@@ -324,6 +324,31 @@ def test_ntt_roundtrip_large(native):
         assert buf.raw == packed
 
 
+def test_ntt_above_2_20(native):
+    """Three-pass transforms (2^21 .. 2^26 points, the size axis of kzg.rs:43-44): 2^21 against the CPU oracle, 2^22 by the
+    round trip."""
+    rng = random.Random(21)
+    log_n = 21
+    n = 1 << log_n
+    raw = bytearray(rng.randbytes(n * 32))
+    raw[31::32] = bytes(b & 0x3F for b in raw[31::32])          # < 2^254 < r
+    x = native.unpack_scalars(bytes(raw))
+    for inverse, coset in ((0, 0), (1, 1)):
+        buf = ctypes.create_string_buffer(bytes(raw), n * 32)
+        _chk(native, native.lib().mp_ntt(0, buf, log_n, inverse, coset, None))
+        assert native.unpack_scalars(buf.raw) == cref.ntt(x, log_n, inverse, coset), (inverse, coset)
+    log_n = 22
+    n = 1 << log_n
+    raw = bytearray(rng.randbytes(n * 32))
+    raw[31::32] = bytes(b & 0x3F for b in raw[31::32])
+    for coset in (0, 1):
+        buf = ctypes.create_string_buffer(bytes(raw), n * 32)
+        _chk(native, native.lib().mp_ntt(0, buf, log_n, 0, coset, None))
+        assert buf.raw != bytes(raw)
+        _chk(native, native.lib().mp_ntt(0, buf, log_n, 1, coset, None))
+        assert buf.raw == bytes(raw)
+
+
 # ---- full proofs -------------------------------------------------------------------------------------------------
 def _prove_and_check(native, cs, pk, trap, seeds, rs, ss, oracle_full=True):
     from manta_rs_b200 import groth16 as g16
