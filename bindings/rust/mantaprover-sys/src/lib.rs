@@ -17,6 +17,10 @@ pub struct mp_ctx {
 pub struct mp_batch {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct mp_msm_bases {
+    _private: [u8; 0],
+}
 
 /// `ark_groth16::ProvingKey<Bls12_381>` as a set of borrowed pointers into its `serialize_unchecked` bytes.
 #[repr(C)]
@@ -66,6 +70,8 @@ extern "C" {
     pub fn mp_ctx_create(pk: *const mp_pk_view, r1cs: *const mp_r1cs_view, device: c_int, out: *mut *mut mp_ctx) -> c_int;
     pub fn mp_ctx_destroy(ctx: *mut mp_ctx);
     pub fn mp_prove(ctx: *mut mp_ctx, z: *const u64, r: *const u64, s: *const u64, out_proof: *mut u8) -> c_int;
+    pub fn mp_prove_from_abc(ctx: *mut mp_ctx, z: *const u64, a: *const u64, b: *const u64, c: *const u64, r: *const u64, s: *const u64,
+                             out_proof: *mut u8) -> c_int;
     pub fn mp_prove_batch(ctx: *mut mp_ctx, count: usize, z: *const u64, r: *const u64, s: *const u64, out_proofs: *mut u8) -> c_int;
     pub fn mp_batch_create(ctx: *mut mp_ctx, capacity: usize, out: *mut *mut mp_batch) -> c_int;
     pub fn mp_batch_destroy(b: *mut mp_batch);
@@ -73,6 +79,15 @@ extern "C" {
     pub fn mp_batch_wait(b: *mut mp_batch, out_device_ms: *mut c_float) -> c_int;
     pub fn mp_msm_g1(device: c_int, bases: *const u8, scalars: *const u64, n: usize, out_point: *mut u8, out_device_ms: *mut c_float) -> c_int;
     pub fn mp_msm_g2(device: c_int, bases: *const u8, scalars: *const u64, n: usize, out_point: *mut u8, out_device_ms: *mut c_float) -> c_int;
+    pub fn mp_msm_bases_create(device: c_int, group: c_int, bases: *const u8, n: usize, out: *mut *mut mp_msm_bases) -> c_int;
+    pub fn mp_msm_bases_run(h: *mut mp_msm_bases, scalars: *const u64, n: usize, out_point: *mut u8, out_device_ms: *mut c_float) -> c_int;
+    pub fn mp_msm_bases_destroy(h: *mut mp_msm_bases);
+    pub fn mp_keygen(device: c_int, r1cs: *const mp_r1cs_view, trapdoor: *const u64, h_len: u64, out_pk: *mut u8, out_cap: usize,
+                     out_len: *mut usize) -> c_int;
+    pub fn mp_mpc_initialize(device: c_int, r1cs: *const mp_r1cs_view, tau_powers_g1: *const u8, n_tau_g1: usize, tau_powers_g2: *const u8,
+                             alpha_tau_powers_g1: *const u8, beta_tau_powers_g1: *const u8, beta_g2: *const u8, out_pk: *mut u8,
+                             out_cap: usize, out_len: *mut usize) -> c_int;
+    pub fn mp_group_ntt(device: c_int, group: c_int, points: *mut u8, log_n: u32, inverse: c_int) -> c_int;
     pub fn mp_ntt(device: c_int, data: *mut u64, log_n: u32, inverse: c_int, coset: c_int, out_device_ms: *mut c_float) -> c_int;
     pub fn mp_poseidon_permute(device: c_int, width: c_int, full_rounds: c_int, partial_rounds: c_int, round_keys: *const u64,
                                mds: *const u64, states: *mut u64, count: usize, out_device_ms: *mut c_float) -> c_int;

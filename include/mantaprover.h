@@ -101,6 +101,11 @@ MP_API int mp_ctx_info(const mp_ctx* ctx, uint64_t* n_vars, uint64_t* n_instance
 /* ---- prove: replaces ark_groth16::create_proof(circuit, pk, r, s) behind groth16.rs:597 ---------------------
  * z = full assignment [1, instance.., witness..] (n x 4 limbs), r/s = the two Fr draws of create_random_proof. */
 MP_API int mp_prove(mp_ctx* ctx, const uint64_t* z, const uint64_t r[4], const uint64_t s[4], uint8_t out_proof[MP_PROOF_BYTES]);
+/* The same proof when the host has already evaluated the constraint system (the first step of ark's `witness_map`): a, b, c
+ * are the domain_size evaluations <A_i, z>, <B_i, z>, <C_i, z> (canonical, zero padded; a carries z_j at rows K + j, the
+ * "dummy input constraints"), so the context's matrices are not consulted. */
+MP_API int mp_prove_from_abc(mp_ctx* ctx, const uint64_t* z, const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t r[4],
+                             const uint64_t s[4], uint8_t out_proof[MP_PROOF_BYTES]);
 /* count independent proofs against the same context; z is count x n x 4 limbs contiguous, r/s count x 4. */
 MP_API int mp_prove_batch(mp_ctx* ctx, size_t count, const uint64_t* z, const uint64_t* r, const uint64_t* s,
                    uint8_t* out_proofs /* count x 192 */);

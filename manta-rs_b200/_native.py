@@ -48,6 +48,7 @@ SYMBOLS = {
     "mp_ctx_destroy": (None, [_V]),
     "mp_ctx_info": (_I, [_V, _V, _V, _V, _V]),
     "mp_prove": (_I, [_V, _V, _V, _V, _V]),
+    "mp_prove_from_abc": (_I, [_V, _V, _V, _V, _V, _V, _V, _V]),
     "mp_prove_batch": (_I, [_V, _SZ, _V, _V, _V, _V]),
     "mp_batch_create": (_I, [_V, _SZ, _V]),
     "mp_batch_create_ex": (_I, [_V, _SZ, _I, _V]),

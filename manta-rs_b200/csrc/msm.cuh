@@ -103,6 +103,7 @@ struct MsmBaWs {
     void* tot = nullptr;       // F per thread: product of its denominators, then its inverse
     void* pre2 = nullptr;      // F per thread: second-level prefix products
     size_t cap_pairs = 0, cap_threads = 0;  // slots behind prefix/desc and tot/pre2 (sized for every count <= capacity)
+    int round_limit = 0;                    // > 0: launch only this many tree levels (msm_ba_rounds_needed), 0: every provisioned level
     // optional: recorded around the round-1 k_ba_bwd launch of the bucket trees (the dominant kernel of a proof)
     cudaEvent_t ev_bwd0 = nullptr, ev_bwd1 = nullptr;
 };
@@ -110,6 +111,7 @@ size_t msm_ba_ws_bytes(const MsmGeom* geoms, int n_jobs, size_t batch, bool g2);
 void msm_ba_ws_bind(MsmBaWs& ws, const MsmGeom* geoms, int n_jobs, size_t batch, bool g2, void* mem);
 // host-only: {pairs, threads} a live `count` needs and {pairs, threads} a workspace sized for `cap` provides
 void msm_ba_ws_demand(const MsmGeom* geoms, int n_jobs, size_t cap, size_t count, uint64_t out[4]);
+int msm_ba_rounds_needed(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_t st, int* out_rounds);
 // ba == nullptr selects the XYZZ accumulation (jobs[].partial), otherwise batched affine (jobs[].pbuf)
 int msm_accumulate_g1(const MsmJob* jobs, int n_jobs, size_t batch, const MsmBaWs* ba, cudaStream_t st);
 int msm_accumulate_g2(const MsmJob* jobs, int n_jobs, size_t batch, const MsmBaWs* ba, cudaStream_t st);

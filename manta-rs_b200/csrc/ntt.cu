@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "ntt.cuh"
+#include "tma.cuh"
 
 namespace mp {
 
@@ -39,31 +40,9 @@ struct NttArgs {
 
 MP_DEV unsigned brev_bits(unsigned p, unsigned lg) { return lg ? (__brev(p) >> (32 - lg)) : 0u; }
 
-// ---- TMA bulk copies (cp.async.bulk, global -> shared, completion on an mbarrier) -------------------------------
+// ---- TMA bulk copies (tma.cuh) ---------------------------------------------------------------------------------------
 // A tile of either pass is a set of contiguous global rows (8 KiB rows in pass 2, 256-byte rows in pass 1): each row
 // is one bulk copy issued by a lane of warp 0, so the copy engine - not 256 threads doing LDG + STS - stages the tile.
-MP_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-MP_DEV void mbar_init(uint64_t* bar, uint32_t arrivals) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-MP_DEV void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-MP_DEV void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-MP_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done)
-                     : "r"(smem_u32(bar)), "r"(parity)
-                     : "memory");
-    } while (!done);
-}
 
 // In-SMEM decimation-in-frequency transform of `seqs` sequences of 2^lg points.
 // element (j, c) at s[(j * sj + c * sc) * 8]; twiddle w_np^e at tws[e * 8].  Leaves bit-reversed order.

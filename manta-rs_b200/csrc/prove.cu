@@ -20,6 +20,8 @@
 #include <new>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "msm.cuh"
 #include "ntt.cuh"
 
@@ -33,6 +35,16 @@ constexpr int N_EXTRA = 4;   // r, s, -rs, 1
 enum Phase { PH_UPLOAD = 0, PH_PREP, PH_G2, PH_WITNESS_MAP, PH_SORT, PH_ACC_G1, PH_REDUCE, PH_FINISH, PH_COUNT };
 static const char* const kPhaseNames[PH_COUNT] = {"upload",   "prep",              "msm_g2(sort+accumulate+reduce)", "witness_map(r1cs+ntt)",
                                                   "msm_sort", "msm_accumulate_g1", "msm_reduce_g1",                  "finish"};
+
+// NVTX ranges around the enqueue of every phase, named like the timers of ark-groth16 0.3 `create_proof_with_reduction`
+// ("Groth16::Prover" > "R1CS to QAP witness map", "Compute A", "Compute B in G1", "Compute B in G2", "Compute C", "Finish C"),
+// so a timeline of this library lines up with the reference's `print-trace` output.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 }  // namespace mp
 
@@ -84,6 +96,7 @@ struct mp_batch {
     float phase_ms[PH_COUNT] = {};
     uint64_t launches = 0;
     bool ran = false, in_flight = false, upload_timed = false;
+    bool abc_supplied = false;  // mp_prove_from_abc: the evaluation vectors are already in `abc`, skip the CSR products
     size_t device_bytes = 0;  // device memory behind this batch object (every per-proof buffer is allocated at creation)
 };
 
@@ -142,10 +155,9 @@ MP_COLD XYZZ<F> scalar_mul_affine(const Affine<F>& p, const uint32_t* k) {
 // memory as 48-byte "slots" and every LEVEL of a formula - the field products that do not depend on each other - runs as
 // ONE multiplication issued by the whole warp, each lane on its own pair of operands:
 //   doubling (2008-s-1)  9 products -> 3 levels      addition (add-2008-s) 14 products -> 4 levels
-// Level programs live in constant memory: per lane two operands (a slot, twice / three times a slot, or a difference
-// of two slots), a destination and an optional subtrahend applied to the product.  GLV (k = k1 + k2 lambda, 128-bit halves,
-// table {P, phi P, P + phi P}) halves the doublings; the table stays in XYZZ because a full addition has the same depth as
-// a mixed one once its products spread over the lanes.
+// Level programs live in constant memory (per lane: two operand slots and a destination); the few sums and differences between
+// levels are one-lane steps.  GLV (k = k1 + k2 lambda, 128-bit halves, table {P, phi P, P + phi P}) halves the doublings; the
+// table stays in XYZZ because a full addition has the same depth as a mixed one once its products spread over the lanes.
 // The formulas have no branches: an addition whose operands are equal (possible for chosen scalars) or whose accumulator
 // is the point at infinity (only for points outside the prime-order subgroup) raises a flag, and the whole product is then
 // redone by one lane with the complete XYZZ routines.
@@ -155,83 +167,78 @@ constexpr int TMP = 4;      // slots 4..19: temporaries
 constexpr int TAB = 20;     // slots 20..31: table entries P, phi P, P + phi P (4 slots each)
 constexpr int SLOTS = 32;
 constexpr int REL = 64;     // operand indices >= REL address the selected table entry: slot = entry + (index - REL)
-enum Mode : uint8_t { M_S = 0, M_2S = 1, M_3S = 2, M_SUB = 3 };
-struct Opnd { uint8_t i, mode, j; };
-struct MulOp { Opnd a, b; uint8_t dst, post, chk; };   // post: 0xff = none, else result -= slot[post]; chk: 1 = flag if a == 0, 2 = flag if b == 0
 constexpr uint8_t NONE = 0xff;
 constexpr int T(int k) { return TMP + k; }
-// doubling of the accumulator: U = 2Y, V = U^2, W = U V, S = X V, M = 3 X^2, X3 = M^2 - 2S, Y3 = M (S - X3) - W Y, ZZ3 = V ZZ, ZZZ3 = W ZZZ
-__constant__ MulOp DBL1[4] = {{{1, M_2S, 0}, {1, M_2S, 0}, T(0), NONE, 0},     // V
-                              {{0, M_S, 0}, {0, M_S, 0}, T(1), NONE, 0},       // XX
-                              {{1, M_2S, 0}, {1, M_S, 0}, T(2), NONE, 0},      // U Y
-                              {{1, M_2S, 0}, {3, M_S, 0}, T(3), NONE, 0}};     // U ZZZ
-__constant__ MulOp DBL2[5] = {{{0, M_S, 0}, {T(0), M_S, 0}, T(4), NONE, 0},          // S = X V
-                              {{T(1), M_3S, 0}, {T(1), M_3S, 0}, T(5), NONE, 0},     // M^2
-                              {{T(0), M_S, 0}, {T(2), M_S, 0}, T(6), NONE, 0},       // W Y = V (U Y)
-                              {{T(0), M_S, 0}, {2, M_S, 0}, 2, NONE, 0},             // ZZ3
-                              {{T(0), M_S, 0}, {T(3), M_S, 0}, 3, NONE, 0}};         // ZZZ3 = V (U ZZZ)
-// between: X3 = M^2 - 2 S -> slot 0
-__constant__ MulOp DBL3[1] = {{{T(1), M_3S, 0}, {T(4), M_SUB, 0}, 1, T(6), 0}};      // Y3 = M (S - X3) - W Y
-// accumulator + table entry E = (x2, y2, zz2, zzz2) (add-2008-s)
-__constant__ MulOp ADD1[6] = {{{0, M_S, 0}, {REL + 2, M_S, 0}, T(0), NONE, 2},       // U1 = X zz2        (flag: table entry at infinity)
-                              {{REL + 0, M_S, 0}, {2, M_S, 0}, T(1), NONE, 2},       // U2 = x2 ZZ        (flag: accumulator at infinity)
-                              {{1, M_S, 0}, {REL + 3, M_S, 0}, T(2), NONE, 0},       // S1 = Y zzz2
-                              {{REL + 1, M_S, 0}, {3, M_S, 0}, T(3), NONE, 0},       // S2 = y2 ZZZ
-                              {{2, M_S, 0}, {REL + 2, M_S, 0}, T(4), NONE, 0},       // ZZ zz2
-                              {{3, M_S, 0}, {REL + 3, M_S, 0}, T(5), NONE, 0}};      // ZZZ zzz2
-// P = U2 - U1, R = S2 - S1
-__constant__ MulOp ADD2[4] = {{{T(1), M_SUB, T(0)}, {T(1), M_SUB, T(0)}, T(6), NONE, 1},   // PP              (flag: P == 0, equal x)
-                              {{T(3), M_SUB, T(2)}, {T(3), M_SUB, T(2)}, T(7), NONE, 0},   // RR
-                              {{T(1), M_SUB, T(0)}, {T(5), M_S, 0}, T(8), NONE, 0},        // P ZZZ zzz2
-                              {{T(1), M_SUB, T(0)}, {T(2), M_S, 0}, T(9), NONE, 0}};       // S1 P
-__constant__ MulOp ADD3[5] = {{{T(1), M_SUB, T(0)}, {T(6), M_S, 0}, T(10), NONE, 0},       // PPP
-                              {{T(0), M_S, 0}, {T(6), M_S, 0}, T(11), NONE, 0},            // Q = U1 PP
-                              {{T(4), M_S, 0}, {T(6), M_S, 0}, 2, NONE, 0},                // ZZ3
-                              {{T(8), M_S, 0}, {T(6), M_S, 0}, 3, NONE, 0},                // ZZZ3
-                              {{T(9), M_S, 0}, {T(6), M_S, 0}, T(12), NONE, 0}};           // S1 PPP
-// between: X3 = RR - PPP - 2 Q -> slot 0
-__constant__ MulOp ADD4[1] = {{{T(3), M_SUB, T(2)}, {T(11), M_SUB, 0}, 1, T(12), 0}};      // Y3 = R (Q - X3) - S1 PPP
+// One level = up to 6 independent products; lane i multiplies slot a[i] by slot b[i] into slot d[i] (every lane runs the same
+// code, operands are plain slots: the sums and differences a formula needs between levels are separate one-lane steps).
+// post: slot subtracted from the product of a one-lane level (NONE = nothing).
+struct Level { uint8_t n, post, a[6], b[6], d[6]; };
+// doubling of the accumulator (dbl-2008-s-1, a = 0): U = 2Y, V = U^2, W = U V, S = X V, M = 3 X^2, X3 = M^2 - 2S,
+// Y3 = M (S - X3) - W Y, ZZ3 = V ZZ, ZZZ3 = W ZZZ.   T7 = U, T8 = M, T9 = S - X3
+__constant__ Level DBL1 = {4, NONE, {T(7), 0, T(7), T(7)}, {T(7), 0, 1, 3}, {T(0), T(1), T(2), T(3)}};                    // V, XX, U Y, U ZZZ
+__constant__ Level DBL2 = {5, NONE, {0, T(8), T(0), T(0), T(0)}, {T(0), T(8), T(2), 2, T(3)}, {T(4), T(5), T(6), 2, 3}};  // S, M^2, W Y, ZZ3, ZZZ3
+__constant__ Level DBL3 = {1, T(6), {T(8)}, {T(9)}, {1}};                                                                // Y3 = M (S - X3) - W Y
+// accumulator + table entry E = (x2, y2, zz2, zzz2) (add-2008-s).   T13 = P = U2 - U1, T14 = R = S2 - S1, T15 = Q - X3
+__constant__ Level ADD1 = {6, NONE, {0, REL + 0, 1, REL + 1, 2, 3}, {REL + 2, 2, REL + 3, 3, REL + 2, REL + 3},
+                           {T(0), T(1), T(2), T(3), T(4), T(5)}};                                 // U1, U2, S1, S2, ZZ zz2, ZZZ zzz2
+__constant__ Level ADD2 = {4, NONE, {T(13), T(14), T(13), T(13)}, {T(13), T(14), T(5), T(2)}, {T(6), T(7), T(8), T(9)}};   // PP, RR, P ZZZ zzz2, S1 P
+__constant__ Level ADD3 = {5, NONE, {T(13), T(0), T(4), T(8), T(9)}, {T(6), T(6), T(6), T(6), T(6)}, {T(10), T(11), 2, 3, T(12)}};  // PPP, Q, ZZ3, ZZZ3, S1 PPP
+__constant__ Level ADD4 = {1, T(12), {T(14)}, {T(15)}, {1}};                                                              // Y3 = R (Q - X3) - S1 PPP
 
 MP_DEV Fq ld(const uint32_t* s, int i) { return Fq::load(s + 12 * i); }
 MP_DEV void st(uint32_t* s, int i, const Fq& v) { v.store(s + 12 * i); }
-MP_DEV Fq fetch(const uint32_t* s, const Opnd& o, int entry) {
-    const int i = o.i >= REL ? entry + (o.i - REL) : o.i;
-    Fq v = ld(s, i);
-    if (o.mode == M_2S) v = v.dbl();
-    else if (o.mode == M_3S) v = v.dbl() + v;
-    else if (o.mode == M_SUB) v = v - ld(s, o.j >= REL ? entry + (o.j - REL) : o.j);
-    return v;
-}
-// one level: lanes < n multiply their operand pairs; all loads happen before any store of the level
-MP_DEV void level(uint32_t* s, const MulOp* ops, int n, int entry, uint32_t lane, uint32_t* flag) {
+MP_DEV int slot(uint8_t i, int entry) { return i >= REL ? entry + (i - REL) : i; }
+// all loads of a level happen before any of its stores
+MP_DEV void level(uint32_t* s, const Level& L, int entry, uint32_t lane) {
     Fq r;
-    uint8_t dst = 0;
-    if ((int)lane < n) {
-        const MulOp op = ops[lane];
-        const Fq a = fetch(s, op.a, entry), b = fetch(s, op.b, entry);
-        if ((op.chk == 1 && a.is_zero()) || (op.chk == 2 && b.is_zero())) *flag = 1;
-        r = a * b;
-        if (op.post != NONE) r = r - ld(s, op.post);
-        dst = op.dst;
+    int dst = 0;
+    if (lane < L.n) {
+        r = ld(s, slot(L.a[lane], entry)) * ld(s, slot(L.b[lane], entry));
+        if (L.post != NONE) r = r - ld(s, L.post);
+        dst = L.d[lane];
     }
     __syncwarp();
-    if ((int)lane < n) st(s, dst, r);
+    if (lane < L.n) st(s, dst, r);
     __syncwarp();
 }
-MP_DEV void dbl(uint32_t* s, uint32_t lane, uint32_t* flag) {
-    level(s, DBL1, 4, 0, lane, flag);
-    level(s, DBL2, 5, 0, lane, flag);
-    if (lane == 0) st(s, 0, ld(s, T(5)) - ld(s, T(4)).dbl());
+MP_DEV void dbl(uint32_t* s, uint32_t lane) {
+    if (lane == 0) st(s, T(7), ld(s, 1).dbl());
     __syncwarp();
-    level(s, DBL3, 1, 0, lane, flag);
+    level(s, DBL1, 0, lane);
+    if (lane == 0) {
+        const Fq xx = ld(s, T(1));
+        st(s, T(8), xx.dbl() + xx);
+    }
+    __syncwarp();
+    level(s, DBL2, 0, lane);
+    if (lane == 0) {
+        const Fq sv = ld(s, T(4)), x3 = ld(s, T(5)) - sv.dbl();
+        st(s, 0, x3);
+        st(s, T(9), sv - x3);
+    }
+    __syncwarp();
+    level(s, DBL3, 0, lane);
 }
+// flag: raised when the formulas do not apply (accumulator at infinity, or equal x-coordinates: doubling / cancellation)
 MP_DEV void add(uint32_t* s, int entry, uint32_t lane, uint32_t* flag) {
-    level(s, ADD1, 6, entry, lane, flag);
-    level(s, ADD2, 4, entry, lane, flag);
-    level(s, ADD3, 5, entry, lane, flag);
-    if (lane == 0) st(s, 0, ld(s, T(7)) - ld(s, T(10)) - ld(s, T(11)).dbl());
+    level(s, ADD1, entry, lane);
+    if (lane == 0) {
+        const Fq p = ld(s, T(1)) - ld(s, T(0));
+        if (p.is_zero() || ld(s, 2).is_zero()) *flag = 1;
+        st(s, T(13), p);
+    } else if (lane == 1) {
+        st(s, T(14), ld(s, T(3)) - ld(s, T(2)));
+    }
     __syncwarp();
-    level(s, ADD4, 1, entry, lane, flag);
+    level(s, ADD2, entry, lane);
+    level(s, ADD3, entry, lane);
+    if (lane == 0) {
+        const Fq q = ld(s, T(11)), x3 = ld(s, T(7)) - ld(s, T(10)) - q.dbl();
+        st(s, 0, x3);
+        st(s, T(15), q - x3);
+    }
+    __syncwarp();
+    level(s, ADD4, entry, lane);
 }
 MP_DEV void copy_point(uint32_t* s, int dst, int src, uint32_t lane) {
     if (lane < 4) st(s, dst + lane, ld(s, src + lane));
@@ -302,7 +309,7 @@ MP_DEV void warp_scalar_mul(uint32_t* s, uint32_t* sc, const XYZZ<Fq>& p, const 
         bool first = true;
         for (; bit >= 0; bit--) {
             const uint32_t sel = ((k1[bit >> 5] >> (bit & 31)) & 1) | (((k2[bit >> 5] >> (bit & 31)) & 1) << 1);
-            if (!first) dbl(s, lane, flag);
+            if (!first) dbl(s, lane);
             if (sel) {
                 const int entry = TAB + 4 * (int)(sel - 1);   // 1: P, 2: phi P, 3: P + phi P
                 if (first) copy_point(s, ACC, entry, lane);
@@ -315,7 +322,7 @@ MP_DEV void warp_scalar_mul(uint32_t* s, uint32_t* sc, const XYZZ<Fq>& p, const 
         while (bit >= 0 && !((sc[bit >> 5] >> (bit & 31)) & 1)) bit--;
         copy_point(s, ACC, TAB, lane);
         for (bit--; bit >= 0; bit--) {
-            dbl(s, lane, flag);
+            dbl(s, lane);
             if ((sc[bit >> 5] >> (bit & 31)) & 1) add(s, TAB, lane, flag);
         }
     }
@@ -615,6 +622,7 @@ static int batch_enqueue(mp_batch* b) {
     const size_t cnt = b->count;
     if (cnt == 0) return MP_OK;
     MP_TRY(use_device(c->device));
+    NvtxRange whole("Groth16::Prover");
     cudaStream_t st = b->st;
     const uint64_t launches0 = kernel_launch_counter();
     const size_t g1w = XYZZ<Fq>::WORDS * 4, g2w = XYZZ<Fq2>::WORDS * 4;
@@ -644,12 +652,17 @@ static int batch_enqueue(mp_batch* b) {
     const bool g2_side = b->overlap && cnt <= 16;
     cudaStream_t sg2 = g2_side ? b->st2 : st;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_G2], st));
+    nvtxRangePushA("Compute B in G2");
     if (g2_side) {
         MP_CUDA_TRY(cudaEventRecord(b->ev_tail_fork, st));  // z' complete
         MP_CUDA_TRY(cudaStreamWaitEvent(sg2, b->ev_tail_fork, 0));
     }
     MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_b, c->valid_b.as<uint32_t>(), sg2));
     if (g2_side) MP_CUDA_TRY(cudaEventRecord(b->ev_sort_b, sg2));  // the B1 job of the G1 launch reads the B list
+    // one or two proofs: find out how many tree levels are populated instead of walking all the provisioned ones
+    const bool trim_rounds = b->use_ba && cnt <= 2;
+    b->ba_g1.round_limit = b->ba_g2.round_limit = 0;
+    if (trim_rounds) MP_TRY(msm_ba_rounds_needed(g2, 1, cnt, sg2, &b->ba_g2.round_limit));
     MP_TRY(msm_accumulate_g2(g2, 1, cnt, ba2, sg2));
     MP_TRY(msm_reduce_heavy_g2(g2, 1, cnt, ba2, sg2));
     if (b->overlap && !g2_side) {
@@ -658,17 +671,22 @@ static int batch_enqueue(mp_batch* b) {
     }
     MP_TRY(msm_reduce_tail_g2(g2, 1, cnt, ba2, st_tail));
     if (b->overlap) MP_CUDA_TRY(cudaEventRecord(b->ev_g2, st_tail));
+    nvtxRangePop();
     // ---- witness map
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_WITNESS_MAP], st));
-    MP_TRY(r1cs_eval(c->r1cs, b->z_mont.p, c->zlen, cnt, c->m, b->abc.p, st));
+    nvtxRangePushA("R1CS to QAP witness map");
+    if (!b->abc_supplied) MP_TRY(r1cs_eval(c->r1cs, b->z_mont.p, c->zlen, cnt, c->m, b->abc.p, st));
     MP_TRY(witness_map_run(c->dom, b->abc.p, b->s1.p, b->s2.p, cnt, b->h_canon.p, c->m, st));
+    nvtxRangePop();
     // ---- G1 MSMs
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_SORT], st));
+    nvtxRangePushA("Compute A, Compute B in G1, Compute C (H and L queries)");
     MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_a, c->valid_a.as<uint32_t>(), st));
     MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_l, c->valid_l.as<uint32_t>(), st));
     MP_TRY(msm_sort(b->gh, b->h_canon.as<uint32_t>(), (size_t)c->m * 8, cnt, b->sort_h, c->valid_h.as<uint32_t>(), st));
     if (g2_side) MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_sort_b, 0));
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_ACC_G1], st));
+    if (trim_rounds) MP_TRY(msm_ba_rounds_needed(g1, 4, cnt, st, &b->ba_g1.round_limit));
     MP_TRY(msm_accumulate_g1(g1, 4, cnt, ba1, st));
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_REDUCE], st));
     MP_TRY(msm_reduce_heavy_g1(g1, 4, cnt, ba1, st));
@@ -676,8 +694,10 @@ static int batch_enqueue(mp_batch* b) {
     c->last_heavy = b->ev_heavy;
     c->last_heavy_owner = b;
     MP_TRY(msm_reduce_tail_g1(g1, 4, cnt, ba1, st));
+    nvtxRangePop();
     if (b->overlap) MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_g2, 0));
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_FINISH], st));
+    NvtxRange fin("Finish C");
     k_prove_finish<<<(unsigned)cnt, FINISH_THREADS, 0, st>>>(b->res_g1.as<XYZZ<Fq>>(), b->res_g2.as<XYZZ<Fq2>>(), b->rs.as<uint32_t>(),
                                                              (uint32_t)cnt, c->glv ? 1 : 0, b->proofs.as<uint8_t>());
     MP_KERNEL_CHECK();
@@ -966,6 +986,24 @@ int mp_debug_prove_ba_demand(uint32_t n_vars, uint32_t domain_size, size_t capac
     if (g2) msm_ba_ws_demand(&gz, 1, capacity, count, out);
     else msm_ba_ws_demand(g1, 4, capacity, count, out);
     return MP_OK;
+}
+
+int mp_prove_from_abc(mp_ctx* ctx, const uint64_t* z, const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t r[4],
+                      const uint64_t s[4], uint8_t out_proof[MP_PROOF_BYTES]) {
+    if (!ctx || !z || !a || !b || !c || !r || !s || !out_proof) return MP_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->single_mu);
+    if (!ctx->single) MP_TRY(mp_batch_create(ctx, 1, &ctx->single));
+    mp_batch* bt = ctx->single;
+    MP_TRY(mp_batch_upload(bt, 1, z, r, s));
+    const size_t vec = ctx->m * 32;
+    const uint64_t* src[3] = {a, b, c};
+    for (int i = 0; i < 3; i++) MP_CUDA_TRY(cudaMemcpyAsync(bt->abc.as<char>() + i * vec, src[i], vec, cudaMemcpyHostToDevice, bt->st));
+    MP_TRY(fr_to_mont(bt->abc.p, bt->abc.p, 3 * ctx->m, bt->st));
+    bt->abc_supplied = true;
+    int rc = mp_batch_run(bt, nullptr);
+    bt->abc_supplied = false;
+    MP_TRY(rc);
+    return mp_batch_download(bt, out_proof);
 }
 
 int mp_witness_map(mp_ctx* ctx, const uint64_t* z, uint64_t* out_h) {

@@ -222,3 +222,74 @@ class Groth16:
             return [Proof(out.raw[i * nat.PROOF_BYTES:(i + 1) * nat.PROOF_BYTES]) for i in range(len(compilers))]
         except nat.NativeError as e:
             raise Error() from e
+
+
+class ProverPool:
+    """Batch proving over several GPUs of one process with the fault path of SURVEY.md §5: the batch is cut into chunks, every
+    device (one worker thread each, the C ABI call releases the GIL) pulls chunks from one queue, and when a device fails
+    (any non-zero return code of the library: CUDA error, out of memory, lost device) it is retired and its chunk is
+    re-queued for the surviving devices.  Proofs are independent units, so the result does not depend on
+    which device produced which proof.  Raises `Error` only when every device has failed."""
+
+    def __init__(self, context: ProvingContext, devices, chunk: int = 128, prove_chunk=None):
+        self.context = context
+        self.devices = list(devices)
+        self.chunk = max(1, chunk)
+        self.failed = {}            # device -> the error that retired it
+        self._prove_chunk = prove_chunk or self._native_chunk
+
+    def _native_chunk(self, device, compilers, rs, ss):
+        mats = compilers[0].matrices
+        h = self.context.native(mats, device)
+        z = b"".join(nat.pack_scalars(c.assignment) for c in compilers)
+        out = ctypes.create_string_buffer(nat.PROOF_BYTES * len(compilers))
+        nat.check(nat.lib().mp_prove_batch(h, len(compilers), z, nat.pack_scalars(rs), nat.pack_scalars(ss), out))
+        return [out.raw[i * nat.PROOF_BYTES:(i + 1) * nat.PROOF_BYTES] for i in range(len(compilers))]
+
+    def prove_many_with_randomness(self, compilers, rs, ss):
+        import queue
+        import threading
+        n = len(compilers)
+        if n == 0:
+            return []
+        if any(c.matrices is not compilers[0].matrices for c in compilers):
+            raise Error()
+        work = queue.Queue()
+        for lo in range(0, n, self.chunk):
+            work.put(list(range(lo, min(n, lo + self.chunk))))
+        results = [None] * n
+        lock = threading.Lock()
+        pending = [work.qsize()]
+
+        def worker(device):
+            while True:
+                with lock:
+                    if pending[0] == 0 or device in self.failed:
+                        return
+                try:
+                    idx = work.get(timeout=0.05)
+                except queue.Empty:
+                    continue
+                try:
+                    proofs = self._prove_chunk(device, [compilers[i] for i in idx], [rs[i] for i in idx], [ss[i] for i in idx])
+                    if len(proofs) != len(idx) or any(len(p) != nat.PROOF_BYTES for p in proofs):
+                        raise nat.NativeError(2, "malformed result", f"device {device}")
+                except nat.NativeError as e:
+                    with lock:
+                        self.failed[device] = e
+                    work.put(idx)           # re-queue for the surviving devices
+                    return
+                with lock:
+                    for i, p in zip(idx, proofs):
+                        results[i] = Proof(p)
+                    pending[0] -= 1
+
+        live = [d for d in self.devices if d not in self.failed]
+        threads = [threading.Thread(target=worker, args=(d,), daemon=True) for d in live]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if any(r is None for r in results):
+            raise Error()           # every device failed
+        return results

@@ -479,6 +479,55 @@ def test_finish_ladder_special_scalars(native):
     ctx.close()
 
 
+def test_fwd_tma_form_matches(native):
+    """The TMA-staged forward pass of the batched-affine rounds (MP_FWD_TMA=1, kept as a measured experiment) gives the same
+    bytes as the default LDG form: run in a fresh process because the choice is read once per process."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, ctypes, random; sys.path.insert(0, 'tests')\n"
+        "from helpers import cref, BLS12_381 as C\n"
+        "from manta_rs_b200 import _native as nat\n"
+        "rng = random.Random(3)\n"
+        "for group, n in ((1, 3000), (2, 500)):\n"
+        "    pb = 96 * group\n"
+        "    bases = cref.fixed_base(group, [rng.randrange(1, C.r) for _ in range(n)])\n"
+        "    bases = bases[:pb * 5] + bases[pb * 4:pb * 5] * 3 + bases[pb * 8:]\n"
+        "    sc = [rng.randrange(C.r) for _ in range(n)]\n"
+        "    sc[5] = sc[6] = sc[7] = sc[4]\n"
+        "    out = ctypes.create_string_buffer(pb)\n"
+        "    fn = nat.lib().mp_msm_g1 if group == 1 else nat.lib().mp_msm_g2\n"
+        "    nat.check(fn(0, bases, nat.pack_scalars(sc), n, out, None))\n"
+        "    assert out.raw == cref.msm(group, bases, sc, threads=4), group\n"
+        "print('ok')\n")
+    env = dict(os.environ, MP_FWD_TMA="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-1500:]
+
+
+def test_prove_from_abc(native):
+    """mp_prove_from_abc: the host evaluates A z, B z, C z itself (ark `witness_map`'s first loop); same proof bytes."""
+    from manta_rs_b200 import groth16 as g16
+    cs = wl.make_r1cs(4, 300, dist="R")
+    pk, trap = oracle_keygen(cs, wl.sample_trapdoor(14))
+    z = wl.make_assignment(cs, 2)
+    r_mod, m = cs.modulus, cs.m
+    ev = lambda rows: [sum(c * z[j] for c, j in row) % r_mod for row in rows] + [0] * (m - cs.K)
+    a, b, c = ev(cs.a), ev(cs.b), ev(cs.c)
+    for j in range(cs.p):
+        a[cs.K + j] = z[j]
+    ctx = g16.ProvingContext.decode(pk)
+    h = ctx.native(g16.R1CS.from_workload(cs, z).matrices)
+    out = ctypes.create_string_buffer(192)
+    P = native.pack_scalars
+    _chk(native, native.lib().mp_prove_from_abc(h, P(z), P(a), P(b), P(c), P([77]), P([88]), out))
+    assert out.raw == trapdoor_proof_bytes(cs, trap, z, 77, 88)
+    _chk(native, native.lib().mp_prove(h, P(z), P([77]), P([88]), out))     # the matrices path still works on the same cached batch
+    assert out.raw == trapdoor_proof_bytes(cs, trap, z, 77, 88)
+    ctx.close()
+
+
 def test_mpc_style_key_with_h_len_m(native):
     """Production keys come from the MPC and carry m (not m - 1) h_query points (mpc.rs:371-377)."""
     cs = wl.make_r1cs(3, 29)

@@ -222,3 +222,47 @@ def test_bench_helpers_scalars_credit_and_dot():
     assert bench.credited_msm_fq_muls(1 << 24) == 2768240640 and bench.credited_msm_fq_muls(1 << 20, True) == 3 * 196083712
     other = bench.random_scalars(5000, 5)
     assert bench.dot_mod(buf, other, r) == sum(a * b for a, b in zip(vals, bench.unpack_fr(other))) % r
+
+
+def test_prover_pool_requeues_the_proofs_of_a_failed_device():
+    """Fault path: a device that fails is retired and its chunk is proved by the survivors; only when every
+    device has failed does the call collapse to the opaque `Error` of groth16.rs:50-60.  CPU stand-ins for the device call."""
+    import threading
+    import time
+    from manta_rs_b200 import groth16 as g16, _native as nat
+
+    class FakeCompiler:
+        matrices = object()
+
+        def __init__(self, i):
+            self.assignment = [1, i]
+
+    comps = [FakeCompiler(i) for i in range(37)]
+    for c in comps:
+        c.matrices = FakeCompiler.matrices
+    rs, ss = list(range(37)), list(range(100, 137))
+    calls, lock = [], threading.Lock()
+
+    def fake(fail_devices):
+        def prove_chunk(device, compilers, r, s):
+            with lock:
+                calls.append((device, [c.assignment[1] for c in compilers]))
+            time.sleep(0.02)            # a chunk takes long enough for every worker to pick one up
+            if device in fail_devices:
+                raise nat.NativeError(2, "CUDA runtime error", "injected")
+            return [bytes([c.assignment[1]]) * 192 for c in compilers]
+        return prove_chunk
+
+    pool = g16.ProverPool(context=None, devices=[0, 1, 2], chunk=5, prove_chunk=fake({1}))
+    out = pool.prove_many_with_randomness(comps, rs, ss)
+    assert [p.to_bytes()[0] for p in out] == list(range(37))
+    assert list(pool.failed) == [1] and sum(1 for d, _ in calls if d == 1) == 1      # retired after its first failure
+    proved = sorted(i for d, idx in calls if d != 1 for i in idx)
+    assert proved == list(range(37))                                                 # the failed chunk was re-proved elsewhere
+    # the pool keeps the device retired on the next call
+    calls.clear()
+    pool.prove_many_with_randomness(comps[:6], rs[:6], ss[:6])
+    assert all(d != 1 for d, _ in calls)
+    with pytest.raises(g16.Error):
+        g16.ProverPool(context=None, devices=[0, 1], chunk=4, prove_chunk=fake({0, 1})).prove_many_with_randomness(comps, rs, ss)
+    assert g16.ProverPool(context=None, devices=[0], prove_chunk=fake(set())).prove_many_with_randomness([], [], []) == []
