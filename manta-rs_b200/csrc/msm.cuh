@@ -103,12 +103,14 @@ struct MsmBaWs {
     void* tot = nullptr;       // F per thread: product of its denominators, then its inverse
     void* pre2 = nullptr;      // F per thread: second-level prefix products
     size_t cap_pairs = 0, cap_threads = 0;  // slots behind prefix/desc and tot/pre2 (sized for every count <= capacity)
+    mutable size_t dom_count = 0;           // vectors covered by the launch the ev_bwd0/1 events bracket (first slab of level 1)
     int round_limit = 0;                    // > 0: launch only this many tree levels (msm_ba_rounds_needed), 0: every provisioned level
     // optional: recorded around the round-1 k_ba_bwd launch of the bucket trees (the dominant kernel of a proof)
     cudaEvent_t ev_bwd0 = nullptr, ev_bwd1 = nullptr;
 };
 size_t msm_ba_ws_bytes(const MsmGeom* geoms, int n_jobs, size_t batch, bool g2);
 void msm_ba_ws_bind(MsmBaWs& ws, const MsmGeom* geoms, int n_jobs, size_t batch, bool g2, void* mem);
+size_t msm_ba_slab(size_t batch, bool g2);   // vectors the round scratch of a batch of `batch` is sized for
 // host-only: {pairs, threads} a live `count` needs and {pairs, threads} a workspace sized for `cap` provides
 void msm_ba_ws_demand(const MsmGeom* geoms, int n_jobs, size_t cap, size_t count, uint64_t out[4]);
 int msm_ba_rounds_needed(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_t st, int* out_rounds);

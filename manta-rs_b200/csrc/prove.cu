@@ -83,6 +83,12 @@ struct mp_batch {
     MsmSortWs sort_a, sort_b, sort_l, sort_h;  // A | B1+B2 | L | H each get a list without their infinity bases
     DevBuf part_a, part_b1, part_l, part_h, part_b2;
     DevBuf pb_a, pb_b1, pb_l, pb_h, pb_b2, ba_mem_g1, ba_mem_g2;  // batched-affine point buffers and round scratch
+    // Buffers whose lifetimes never overlap share memory in batches of more than 16 proofs, where the whole G2 MSM and the
+    // witness map run on the main stream BEFORE the G1 MSMs: the G2 point buffer is dead once its row/column trees are done
+    // and becomes the H point buffer; the G2 round scratch and the witness-map vectors live inside the G1 round scratch.
+    // (Small batches run the G2 MSM on the second stream beside the G1 work and keep everything separate.)
+    bool aliased = false;
+    void *p_pb_h = nullptr, *p_pb_b2 = nullptr, *p_abc = nullptr, *p_s1 = nullptr, *p_s2 = nullptr;
     MsmBaWs ba_g1, ba_g2;
     MsmGeom gz_rc{}, gh_rc{};                                     // row/column stage of the bucket reduction
     DevBuf rc_a_mem, rc_b_mem, rc_b2_mem, rc_l_mem, rc_h_mem, pbrc_a, pbrc_b1, pbrc_l, pbrc_h, pbrc_b2, resrc_g1, resrc_g2;
@@ -552,9 +558,14 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch*
     MP_TRY(b->z_canon.alloc(cap * c->zlen * 32));
     MP_TRY(b->z_mont.alloc(cap * c->zlen * 32));
     MP_TRY(b->rs.alloc(cap * 64));
-    MP_TRY(b->abc.alloc(cap * 3 * m * 32));
-    MP_TRY(b->s1.alloc(cap * 3 * m * 32));
-    MP_TRY(b->s2.alloc(cap * 3 * m * 32));
+    b->use_ba = msm_use_batched_affine();
+    b->aliased = b->use_ba && cap > 16;
+    if (!b->aliased) {
+        MP_TRY(b->abc.alloc(cap * 3 * m * 32));
+        MP_TRY(b->s1.alloc(cap * 3 * m * 32));
+        MP_TRY(b->s2.alloc(cap * 3 * m * 32));
+        b->p_abc = b->abc.p; b->p_s1 = b->s1.p; b->p_s2 = b->s2.p;
+    }
     MP_TRY(b->h_canon.alloc(cap * m * 32));
     b->gz = msm_geom(PROVE_C, 1, c->zlen, c->zlen, cap * 2);  // G1 launches carry 4 jobs, the G2 launch one
     b->gh = msm_geom(PROVE_C, 1, (uint32_t)c->m, (uint32_t)c->m, cap * 2);
@@ -563,20 +574,34 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch*
     MP_TRY(msm_sort_ws_alloc(b->sort_l, b->gz, cap, b->sort_l_mem));
     MP_TRY(msm_sort_ws_alloc(b->sort_h, b->gh, cap, b->sort_h_mem));
     const size_t g1w = XYZZ<Fq>::WORDS * 4, g2w = XYZZ<Fq2>::WORDS * 4;
-    b->use_ba = msm_use_batched_affine();
     if (b->use_ba) {
         MP_TRY(b->pb_a.alloc(cap * b->gz.p_cap * MP_G1_BYTES));
         MP_TRY(b->pb_b1.alloc(cap * b->gz.p_cap * MP_G1_BYTES));
         MP_TRY(b->pb_l.alloc(cap * b->gz.p_cap * MP_G1_BYTES));
-        MP_TRY(b->pb_h.alloc(cap * b->gh.p_cap * MP_G1_BYTES));
-        MP_TRY(b->pb_b2.alloc(cap * b->gz.p_cap * MP_G2_BYTES));
         const MsmGeom geoms_g1[4] = {b->gz, b->gz, b->gz, b->gh};
-        MP_TRY(b->ba_mem_g1.alloc(msm_ba_ws_bytes(geoms_g1, 4, cap, false)));
+        const size_t pbh = cap * b->gh.p_cap * MP_G1_BYTES, pbb2 = cap * b->gz.p_cap * MP_G2_BYTES;
+        const size_t ba1 = msm_ba_ws_bytes(geoms_g1, 4, cap, false), ba2 = msm_ba_ws_bytes(&b->gz, 1, cap, true);
+        const size_t wm = (cap * 3 * m * 32 + 255) & ~size_t(255);
+        if (b->aliased) {
+            MP_TRY(b->pb_h.alloc(std::max(pbh, pbb2)));
+            b->p_pb_h = b->p_pb_b2 = b->pb_h.p;
+            MP_TRY(b->ba_mem_g1.alloc(std::max(std::max(ba1, ba2), 3 * wm)));
+            msm_ba_ws_bind(b->ba_g2, &b->gz, 1, cap, true, b->ba_mem_g1.p);
+            b->p_abc = b->ba_mem_g1.p;
+            b->p_s1 = b->ba_mem_g1.as<char>() + wm;
+            b->p_s2 = b->ba_mem_g1.as<char>() + 2 * wm;
+        } else {
+            MP_TRY(b->pb_h.alloc(pbh));
+            MP_TRY(b->pb_b2.alloc(pbb2));
+            b->p_pb_h = b->pb_h.p;
+            b->p_pb_b2 = b->pb_b2.p;
+            MP_TRY(b->ba_mem_g1.alloc(ba1));
+            MP_TRY(b->ba_mem_g2.alloc(ba2));
+            msm_ba_ws_bind(b->ba_g2, &b->gz, 1, cap, true, b->ba_mem_g2.p);
+        }
         msm_ba_ws_bind(b->ba_g1, geoms_g1, 4, cap, false, b->ba_mem_g1.p);
         b->ba_g1.ev_bwd0 = b->ev_dom0;
         b->ba_g1.ev_bwd1 = b->ev_dom1;
-        MP_TRY(b->ba_mem_g2.alloc(msm_ba_ws_bytes(&b->gz, 1, cap, true)));
-        msm_ba_ws_bind(b->ba_g2, &b->gz, 1, cap, true, b->ba_mem_g2.p);
         b->gz_rc = msm_geom_rc(b->gz);
         b->gh_rc = msm_geom_rc(b->gh);
         MP_TRY(msm_sort_ws_alloc(b->rc_a, b->gz_rc, cap, b->rc_a_mem));
@@ -640,16 +665,16 @@ static int batch_enqueue(mp_batch* b) {
         {b->gz, b->sort_a, c->tab_a.p, b->part_a.p, res1, b->red_a.p, b->pb_a.p, b->gz_rc, b->rc_a, b->pbrc_a.p, rrc1},
         {b->gz, b->sort_b, c->tab_b1.p, b->part_b1.p, res1 + cnt * g1w, b->red_b1.p, b->pb_b1.p, b->gz_rc, b->rc_b, b->pbrc_b1.p, rrc1 + 2 * cnt * g1w},
         {b->gz, b->sort_l, c->tab_l.p, b->part_l.p, res1 + 2 * cnt * g1w, b->red_l.p, b->pb_l.p, b->gz_rc, b->rc_l, b->pbrc_l.p, rrc1 + 4 * cnt * g1w},
-        {b->gh, b->sort_h, c->tab_h.p, b->part_h.p, res1 + 3 * cnt * g1w, b->red_h.p, b->pb_h.p, b->gh_rc, b->rc_h, b->pbrc_h.p, rrc1 + 6 * cnt * g1w},
+        {b->gh, b->sort_h, c->tab_h.p, b->part_h.p, res1 + 3 * cnt * g1w, b->red_h.p, b->p_pb_h, b->gh_rc, b->rc_h, b->pbrc_h.p, rrc1 + 6 * cnt * g1w},
     };
-    MsmJob g2[1] = {{b->gz, b->sort_b, c->tab_b2.p, b->part_b2.p, b->res_g2.p, b->red_b2.p, b->pb_b2.p, b->gz_rc, b->rc_b2, b->pbrc_b2.p, b->resrc_g2.p}};
+    MsmJob g2[1] = {{b->gz, b->sort_b, c->tab_b2.p, b->part_b2.p, b->res_g2.p, b->red_b2.p, b->p_pb_b2, b->gz_rc, b->rc_b2, b->pbrc_b2.p, b->resrc_g2.p}};
     (void)g2w;
     const MsmBaWs* ba1 = b->use_ba ? &b->ba_g1 : nullptr;
     const MsmBaWs* ba2 = b->use_ba ? &b->ba_g2 : nullptr;
     // ---- G2 MSM over the B list.  Large batches: on the main stream (co-running throughput kernels costs ~5 %), only the
     // latency-bound tail of its reduction on the second stream.  Small batches leave the GPU mostly idle and are bound by the
     // per-level latencies of the trees: the whole G2 MSM then runs on the second stream beside the witness map and the G1 MSMs.
-    const bool g2_side = b->overlap && cnt <= 16;
+    const bool g2_side = b->overlap && cnt <= 16 && !b->aliased;
     cudaStream_t sg2 = g2_side ? b->st2 : st;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_G2], st));
     nvtxRangePushA("Compute B in G2");
@@ -675,8 +700,8 @@ static int batch_enqueue(mp_batch* b) {
     // ---- witness map
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_WITNESS_MAP], st));
     nvtxRangePushA("R1CS to QAP witness map");
-    if (!b->abc_supplied) MP_TRY(r1cs_eval(c->r1cs, b->z_mont.p, c->zlen, cnt, c->m, b->abc.p, st));
-    MP_TRY(witness_map_run(c->dom, b->abc.p, b->s1.p, b->s2.p, cnt, b->h_canon.p, c->m, st));
+    if (!b->abc_supplied) MP_TRY(r1cs_eval(c->r1cs, b->z_mont.p, c->zlen, cnt, c->m, b->p_abc, st));
+    MP_TRY(witness_map_run(c->dom, b->p_abc, b->p_s1, b->p_s2, cnt, b->h_canon.p, c->m, st));
     nvtxRangePop();
     // ---- G1 MSMs
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_SORT], st));
@@ -916,10 +941,12 @@ int mp_batch_dominant_kernel(mp_batch* b, float* out_ms, uint64_t* out_additions
         uint64_t total = 0;
         const MsmSortWs* lists[4] = {&b->sort_a, &b->sort_b, &b->sort_l, &b->sort_h};
         const MsmGeom* geoms[4] = {&b->gz, &b->gz, &b->gz, &b->gh};
-        std::vector<uint32_t> host(b->count);
+        // the bracketed launch covers the first slab of the batch (msm_impl.inc: a tree level of a large batch runs in slabs)
+        const size_t covered = b->ba_g1.dom_count ? std::min(b->ba_g1.dom_count, b->count) : b->count;
+        std::vector<uint32_t> host(covered);
         for (int i = 0; i < 4; i++) {
             const size_t row = (size_t)(geoms[i]->ba_rounds + 1) * (PLAN_THREADS + 1);
-            MP_CUDA_TRY(cudaMemcpy2D(host.data(), 4, lists[i]->q + (size_t)(PLAN_THREADS + 1) + PLAN_THREADS, row * 4, 4, b->count,
+            MP_CUDA_TRY(cudaMemcpy2D(host.data(), 4, lists[i]->q + (size_t)(PLAN_THREADS + 1) + PLAN_THREADS, row * 4, 4, covered,
                                      cudaMemcpyDeviceToHost));
             for (uint32_t v : host) total += v;
         }
@@ -978,13 +1005,15 @@ int mp_prove(mp_ctx* ctx, const uint64_t* z, const uint64_t r[4], const uint64_t
     return mp_batch_download(ctx->single, out_proof);
 }
 
-int mp_debug_prove_ba_demand(uint32_t n_vars, uint32_t domain_size, size_t capacity, size_t count, int g2, uint64_t out[4]) {
+int mp_debug_prove_ba_demand(uint32_t n_vars, uint32_t domain_size, size_t capacity, size_t count, int g2, uint64_t out[5]) {
     if (!out || !n_vars || !domain_size || !capacity || count > capacity) return MP_ERR_INVALID_ARG;
     const uint32_t zlen = n_vars + N_EXTRA;
     MsmGeom gz = msm_geom(PROVE_C, 1, zlen, zlen, capacity * 2), gh = msm_geom(PROVE_C, 1, domain_size, domain_size, capacity * 2);
     const MsmGeom g1[4] = {gz, gz, gz, gh};
-    if (g2) msm_ba_ws_demand(&gz, 1, capacity, count, out);
-    else msm_ba_ws_demand(g1, 4, capacity, count, out);
+    const size_t slab = msm_ba_slab(capacity, g2 != 0);
+    if (g2) msm_ba_ws_demand(&gz, 1, slab, std::min(count, slab), out);
+    else msm_ba_ws_demand(g1, 4, slab, std::min(count, slab), out);
+    out[4] = slab;
     return MP_OK;
 }
 

@@ -186,20 +186,24 @@ def test_batched_affine_pair_capacity_covers_worst_case_bucket_loads():
 
 
 def test_batched_affine_round_scratch_covers_every_partial_batch():
-    """A batch object sized for `capacity` proofs re-plans its rounds for the live count (T pairs per thread grows with the
-    pairs of the launch), so a partial batch just under a T threshold needs MORE thread slots than the full one.  The
-    workspace must cover every count <= capacity at the three reference shapes (counts 65..126 of 128 on ToPublic,
-    36..49 of 64 on PrivateTransfer used to overrun it)."""
+    """A batch object re-plans its rounds for the live count (T pairs per thread grows with the pairs of the launch), so a
+    partial batch just under a T threshold needs MORE thread slots than a full one.  The scratch is sized for a slab of the
+    capacity (all of it up to 16 vectors, a quarter / half above) and must cover EVERY count up to that slab at the three
+    reference shapes (ADVICE r1: counts 65..126 of 128 on ToPublic, 36..49 of 64 on PrivateTransfer used to overrun it);
+    larger live counts run a level in several launches of at most one slab."""
     import ctypes
     from manta_rs_b200 import _native as nat
     lib = nat.lib()
-    out = (ctypes.c_uint64 * 4)()
+    out = (ctypes.c_uint64 * 5)()
     shapes = {"to_private": (8253, 1 << 14), "private_transfer": (35175, 1 << 16), "to_public": (27945, 1 << 15), "tiny": (64, 64)}
     for name, (n, m) in shapes.items():
         for cap in (1, 2, 16, 64, 128, 228, 512):
             for g2 in (0, 1):
                 worst = 0.0
-                for count in range(1, cap + 1):
+                nat.check(lib.mp_debug_prove_ba_demand(n, m, cap, cap, g2, out))
+                slab = out[4]
+                assert slab == (cap if cap <= 16 else max(16, -(-cap // (2 if g2 else 4))))
+                for count in range(1, slab + 1):
                     nat.check(lib.mp_debug_prove_ba_demand(n, m, cap, count, g2, out))
                     need_pairs, need_threads, have_pairs, have_threads = out[0], out[1], out[2], out[3]
                     assert need_pairs <= have_pairs and need_threads <= have_threads, (name, cap, count, g2, list(out))
