@@ -211,8 +211,7 @@ MP_API int mp_debug_group_op(int device, int group, int op, const uint8_t* a, co
 MP_API int mp_debug_ba_geometry(int c, int groups, uint32_t n_scalars, int round, uint32_t* out_pair_cap, int* out_rounds,
                                 uint32_t* out_buckets, uint32_t* out_max_entries);
 /* Host-only: batched-affine round scratch of the prover for a circuit with n_vars variables and the given domain size.  A batch
- * object of `capacity` sizes the scratch for a SLAB of out[4] vectors (capacity itself up to 16, a quarter / half of it in
- * G1 / G2 above) and runs a tree level of a larger live count in several launches.  out = {pair slots, thread slots} that
+ * object of `capacity` sizes the scratch for a SLAB of out[4] vectors (capacity itself up to 32, half of it above; MP_BA_SLAB_DIV) and runs a tree level of a larger live count in several launches.  out = {pair slots, thread slots} that
  * min(count, slab) vectors need, then {pair slots, thread slots} the object provides, then the slab.  The CPU tests sweep the
  * counts at the reference shapes (a partial batch re-plans its rounds and can need MORE thread slots than a full one). */
 MP_API int mp_debug_prove_ba_demand(uint32_t n_vars, uint32_t domain_size, size_t capacity, size_t count, int g2, uint64_t out[5]);

@@ -188,7 +188,7 @@ def test_batched_affine_pair_capacity_covers_worst_case_bucket_loads():
 def test_batched_affine_round_scratch_covers_every_partial_batch():
     """A batch object re-plans its rounds for the live count (T pairs per thread grows with the pairs of the launch), so a
     partial batch just under a T threshold needs MORE thread slots than a full one.  The scratch is sized for a slab of the
-    capacity (all of it up to 16 vectors, a quarter / half above) and must cover EVERY count up to that slab at the three
+    capacity (all of it up to 32 vectors, half of it above) and must cover EVERY count up to that slab at the three
     reference shapes (ADVICE r1: counts 65..126 of 128 on ToPublic, 36..49 of 64 on PrivateTransfer used to overrun it);
     larger live counts run a level in several launches of at most one slab."""
     import ctypes
@@ -202,7 +202,7 @@ def test_batched_affine_round_scratch_covers_every_partial_batch():
                 worst = 0.0
                 nat.check(lib.mp_debug_prove_ba_demand(n, m, cap, cap, g2, out))
                 slab = out[4]
-                assert slab == (cap if cap <= 16 else max(16, -(-cap // (2 if g2 else 4))))
+                assert slab == (cap if cap <= 32 else max(32, -(-cap // 2)))
                 for count in range(1, slab + 1):
                     nat.check(lib.mp_debug_prove_ba_demand(n, m, cap, count, g2, out))
                     need_pairs, need_threads, have_pairs, have_threads = out[0], out[1], out[2], out[3]
