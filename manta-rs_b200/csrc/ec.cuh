@@ -221,6 +221,77 @@ struct XYZZ {
     }
 };
 
+// ---- 256-bit global accesses (sm_100: LDG / STG.E.ENL2.256) ---------------------------------------------------------
+// Points are 96 / 192 bytes at 32-byte aligned addresses (window tables, point buffers), so a point moves in 3 / 6 of these
+// instead of 6 / 12 LDG.128, and an x-coordinate in 2 / 3: half the load/store-unit requests and sector look-ups for the
+// random gathers of the batched-affine kernels, which are bound there, not on bytes.  N words, N % 4 == 0; p 32-byte aligned.
+template <int N, bool RO>
+MP_DEV void load_words_256(uint32_t* r, const uint32_t* p) {
+#pragma unroll
+    for (int i = 0; i + 8 <= N; i += 8) {
+        if (RO)
+            asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(r[i]), "=r"(r[i + 1]), "=r"(r[i + 2]), "=r"(r[i + 3]), "=r"(r[i + 4]), "=r"(r[i + 5]), "=r"(r[i + 6]), "=r"(r[i + 7])
+                         : "l"(p + i));
+        else
+            asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(r[i]), "=r"(r[i + 1]), "=r"(r[i + 2]), "=r"(r[i + 3]), "=r"(r[i + 4]), "=r"(r[i + 5]), "=r"(r[i + 6]), "=r"(r[i + 7])
+                         : "l"(p + i)
+                         : "memory");
+    }
+    if (N % 8) {
+        const uint4 v = RO ? __ldg(reinterpret_cast<const uint4*>(p + N - 4)) : *reinterpret_cast<const uint4*>(p + N - 4);
+        r[N - 4] = v.x; r[N - 3] = v.y; r[N - 2] = v.z; r[N - 1] = v.w;
+    }
+}
+template <int N>
+MP_DEV void store_words_256(uint32_t* p, const uint32_t* r) {
+#pragma unroll
+    for (int i = 0; i + 8 <= N; i += 8)
+        asm volatile("st.global.v8.u32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(r[i]), "r"(r[i + 1]), "r"(r[i + 2]), "r"(r[i + 3]), "r"(r[i + 4]),
+                     "r"(r[i + 5]), "r"(r[i + 6]), "r"(r[i + 7]), "l"(p + i)
+                     : "memory");
+    if (N % 8) *reinterpret_cast<uint4*>(p + N - 4) = make_uint4(r[N - 4], r[N - 3], r[N - 2], r[N - 1]);
+}
+MP_DEV Fq field_from_words(const uint32_t* w, const Fq*) {
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = w[i];
+    return r;
+}
+MP_DEV Fq2 field_from_words(const uint32_t* w, const Fq2*) { return {field_from_words(w, (const Fq*)nullptr), field_from_words(w + 12, (const Fq*)nullptr)}; }
+MP_DEV void field_to_words(uint32_t* w, const Fq& v) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) w[i] = v.l[i];
+}
+MP_DEV void field_to_words(uint32_t* w, const Fq2& v) {
+    field_to_words(w, v.c0);
+    field_to_words(w + 12, v.c1);
+}
+// whole affine point / its x-coordinate / a field element, at a 32-byte aligned address
+template <class F, bool RO>
+MP_DEV Affine<F> load_point_256(const uint32_t* p) {
+    constexpr int W = FieldWords<F>::W;
+    uint32_t w[2 * W];
+    load_words_256<2 * W, RO>(w, p);
+    return {field_from_words(w, (const F*)nullptr), field_from_words(w + W, (const F*)nullptr)};
+}
+template <class F, bool RO>
+MP_DEV F load_field_256(const uint32_t* p) {
+    constexpr int W = FieldWords<F>::W;
+    uint32_t w[W];
+    load_words_256<W, RO>(w, p);
+    return field_from_words(w, (const F*)nullptr);
+}
+template <class F>
+MP_DEV void store_point_256(uint32_t* p, const Affine<F>& a) {
+    constexpr int W = FieldWords<F>::W;
+    uint32_t w[2 * W];
+    field_to_words(w, a.x);
+    field_to_words(w + W, a.y);
+    store_words_256<2 * W>(p, w);
+}
+
 using G1Affine = Affine<Fq>;
 using G2Affine = Affine<Fq2>;
 using G1XYZZ = XYZZ<Fq>;

@@ -4,9 +4,9 @@ from collections import defaultdict
 lines = [l for l in open(sys.argv[1]) if not l.startswith('==')]
 rows = [(int(r['ID']), re.sub(r"\(.*", "", r['Kernel Name']), float(r['Metric Value'].replace(',', '')) / 1e6)
         for r in csv.DictReader(lines) if r['Metric Name'] == 'gpu__time_duration.sum']
-ids = [i for i, (_, n, _) in enumerate(rows) if n == 'k_prove_prep']
-start = ids[-1]
-end = [i for i, (_, n, _) in enumerate(rows) if n == 'k_prove_finish' and i > start][0]
+fins = [i for i, (_, n, _) in enumerate(rows) if n == 'k_prove_finish']
+end = fins[-1]                                                      # the last COMPLETE step of the (possibly truncated) list
+start = [i for i, (_, n, _) in enumerate(rows) if n == 'k_prove_prep' and i < end][-1]
 agg = defaultdict(lambda: [0, 0.0])
 tot = 0
 for _, n, v in rows[start:end + 1]:
