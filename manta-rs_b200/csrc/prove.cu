@@ -74,7 +74,8 @@ struct mp_ctx {
 struct mp_batch {
     mp_ctx* ctx = nullptr;
     size_t capacity = 0, count = 0;
-    cudaStream_t st = nullptr, st2 = nullptr;  // main stream; second stream for the G2 path
+    cudaStream_t st = nullptr, st2 = nullptr, st3 = nullptr;  // main stream; G2 path; A / L sorts of a small batch (beside the witness map)
+    cudaEvent_t ev_sort_al = nullptr;
     cudaEvent_t ev_g2_heavy = nullptr, ev_g2 = nullptr, ev_heavy = nullptr, ev_tail_fork = nullptr, ev_sort_b = nullptr;
     cudaEvent_t ev_dom0 = nullptr, ev_dom1 = nullptr;  // around the dominant kernel (round-1 k_ba_bwd<Fq> of the G1 bucket trees)
     bool overlap = true;
@@ -90,6 +91,11 @@ struct mp_batch {
     bool aliased = false;
     void *p_pb_h = nullptr, *p_pb_b2 = nullptr, *p_abc = nullptr, *p_s1 = nullptr, *p_s2 = nullptr;
     MsmBaWs ba_g1, ba_g2;
+    // one or two proofs: the bucket trees of A, B1, L start as soon as their lists are sorted (third stream, beside the witness
+    // map), those of H follow the witness map on the main stream with a round scratch of their own
+    DevBuf ba_mem_h;
+    MsmBaWs ba_h;
+    cudaEvent_t ev_acc_abl = nullptr;
     MsmGeom gz_rc{}, gh_rc{};                                     // row/column stage of the bucket reduction
     DevBuf rc_a_mem, rc_b_mem, rc_b2_mem, rc_l_mem, rc_h_mem, pbrc_a, pbrc_b1, pbrc_l, pbrc_h, pbrc_b2, resrc_g1, resrc_g2;
     MsmSortWs rc_a, rc_b, rc_b2, rc_l, rc_h;  // B1 and B2 keep separate row/column lists: they may run on different streams
@@ -385,14 +391,16 @@ MP_COLD void compress_g2(uint8_t* out, const Affine<Fq2>& p) {
     if (larger) out[95] |= 0x80;
 }
 
-// One block per proof, five warps:
+// G1 half of the proof, one block per proof, four warps:
 //   warp 0: s * g_a          warp 1: r * g1_b          (warp-cooperative ladders)
-//   warp 2: L + H            warp 3: g_a -> affine -> bytes     warp 4: g2_b -> affine -> bytes     (one lane each)
+//   warp 2: L + H            warp 3: g_a -> affine -> bytes       (one lane each)
 // then thread 0 assembles g_c = s g_a + r g1_b + L + H (the -rs delta_1 term rides inside the L MSM) and writes its bytes.
+// The G2 element is finished by k_prove_finish_g2 on the stream of the G2 MSM, so that for a single proof the G2 pipeline
+// (three Fq products deep per multiplication) is no longer in front of the ladders on the critical path.
 // res_g1: [4][batch] XYZZ (A, B1, L, H); res_g2: [batch] XYZZ.
-constexpr int FINISH_THREADS = 160;
-__global__ void __launch_bounds__(FINISH_THREADS) k_prove_finish(const XYZZ<Fq>* __restrict__ res_g1, const XYZZ<Fq2>* __restrict__ res_g2,
-                                                                const uint32_t* __restrict__ rs, uint32_t batch, int glv, uint8_t* proofs) {
+constexpr int FINISH_THREADS = 128;
+__global__ void __launch_bounds__(FINISH_THREADS) k_prove_finish(const XYZZ<Fq>* __restrict__ res_g1, const uint32_t* __restrict__ rs,
+                                                                uint32_t batch, int glv, uint8_t* proofs) {
     __shared__ __align__(16) uint32_t slots[2][coop::SLOTS * 12];
     __shared__ __align__(16) uint32_t scratch[2][16];
     __shared__ __align__(16) uint32_t sh_sa[48], sh_rb[48], sh_lh[48];
@@ -409,10 +417,8 @@ __global__ void __launch_bounds__(FINISH_THREADS) k_prove_finish(const XYZZ<Fq>*
         if (warp == 2) {
             XYZZ<Fq> lh = XYZZ<Fq>::load(res_g1 + (size_t)2 * batch + b).add(XYZZ<Fq>::load(res_g1 + (size_t)3 * batch + b));
             lh.store(sh_lh);
-        } else if (warp == 3) {
-            compress_g1(out, XYZZ<Fq>::load(res_g1 + b).to_affine());
         } else {
-            compress_g2(out + 48, XYZZ<Fq2>::load(res_g2 + b).to_affine());
+            compress_g1(out, XYZZ<Fq>::load(res_g1 + b).to_affine());
         }
     }
     __syncthreads();
@@ -420,6 +426,11 @@ __global__ void __launch_bounds__(FINISH_THREADS) k_prove_finish(const XYZZ<Fq>*
         XYZZ<Fq> c = XYZZ<Fq>::load(sh_sa).add(XYZZ<Fq>::load(sh_rb)).add(XYZZ<Fq>::load(sh_lh));
         compress_g1(out + 144, c.to_affine());
     }
+}
+// g2_b -> affine -> the middle 96 bytes of the proof; one thread per proof
+__global__ void __launch_bounds__(32) k_prove_finish_g2(const XYZZ<Fq2>* __restrict__ res_g2, uint32_t batch, uint8_t* proofs) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch) compress_g2(proofs + (size_t)b * MP_PROOF_BYTES + 48, XYZZ<Fq2>::load(res_g2 + b).to_affine());
 }
 
 // [r] P == infinity for every point of a query (prime-order subgroup membership; enables the GLV ladder of the finishing kernel)
@@ -551,6 +562,9 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch*
     const int prio = high_priority ? prio_greatest : prio_least;
     MP_CUDA_TRY(cudaStreamCreateWithPriority(&b->st, cudaStreamNonBlocking, prio));
     MP_CUDA_TRY(cudaStreamCreateWithPriority(&b->st2, cudaStreamNonBlocking, prio));
+    MP_CUDA_TRY(cudaStreamCreateWithPriority(&b->st3, cudaStreamNonBlocking, prio));
+    MP_CUDA_TRY(cudaEventCreateWithFlags(&b->ev_sort_al, cudaEventDisableTiming));
+    MP_CUDA_TRY(cudaEventCreateWithFlags(&b->ev_acc_abl, cudaEventDisableTiming));
     for (auto& e : b->ev) MP_CUDA_TRY(cudaEventCreate(&e));
     for (cudaEvent_t* e : {&b->ev_g2_heavy, &b->ev_g2, &b->ev_tail_fork, &b->ev_sort_b, &b->ev_dom0, &b->ev_dom1}) MP_CUDA_TRY(cudaEventCreate(e));
     MP_CUDA_TRY(cudaEventCreateWithFlags(&b->ev_heavy, cudaEventDisableTiming));
@@ -600,6 +614,10 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch*
             msm_ba_ws_bind(b->ba_g2, &b->gz, 1, cap, true, b->ba_mem_g2.p);
         }
         msm_ba_ws_bind(b->ba_g1, geoms_g1, 4, cap, false, b->ba_mem_g1.p);
+        if (cap <= 2) {
+            MP_TRY(b->ba_mem_h.alloc(msm_ba_ws_bytes(&b->gh, 1, cap, false)));
+            msm_ba_ws_bind(b->ba_h, &b->gh, 1, cap, false, b->ba_mem_h.p);
+        }
         b->ba_g1.ev_bwd0 = b->ev_dom0;
         b->ba_g1.ev_bwd1 = b->ev_dom1;
         b->gz_rc = msm_geom_rc(b->gz);
@@ -695,8 +713,17 @@ static int batch_enqueue(mp_batch* b) {
         MP_CUDA_TRY(cudaStreamWaitEvent(st_tail, b->ev_g2_heavy, 0));
     }
     MP_TRY(msm_reduce_tail_g2(g2, 1, cnt, ba2, st_tail));
+    k_prove_finish_g2<<<div_up(cnt, 32), 32, 0, st_tail>>>(b->res_g2.as<XYZZ<Fq2>>(), (uint32_t)cnt, b->proofs.as<uint8_t>());
+    MP_KERNEL_CHECK();
     if (b->overlap) MP_CUDA_TRY(cudaEventRecord(b->ev_g2, st_tail));
     nvtxRangePop();
+    // a small batch is latency-bound: the A and L lists only need z', so their sorts run beside the witness map
+    if (g2_side) {
+        MP_CUDA_TRY(cudaStreamWaitEvent(b->st3, b->ev_tail_fork, 0));
+        MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_a, c->valid_a.as<uint32_t>(), b->st3));
+        MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_l, c->valid_l.as<uint32_t>(), b->st3));
+        MP_CUDA_TRY(cudaEventRecord(b->ev_sort_al, b->st3));
+    }
     // ---- witness map
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_WITNESS_MAP], st));
     nvtxRangePushA("R1CS to QAP witness map");
@@ -706,13 +733,30 @@ static int batch_enqueue(mp_batch* b) {
     // ---- G1 MSMs
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_SORT], st));
     nvtxRangePushA("Compute A, Compute B in G1, Compute C (H and L queries)");
-    MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_a, c->valid_a.as<uint32_t>(), st));
-    MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_l, c->valid_l.as<uint32_t>(), st));
+    if (!g2_side) {
+        MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_a, c->valid_a.as<uint32_t>(), st));
+        MP_TRY(msm_sort(b->gz, b->z_canon.as<uint32_t>(), (size_t)c->zlen * 8, cnt, b->sort_l, c->valid_l.as<uint32_t>(), st));
+    }
     MP_TRY(msm_sort(b->gh, b->h_canon.as<uint32_t>(), (size_t)c->m * 8, cnt, b->sort_h, c->valid_h.as<uint32_t>(), st));
-    if (g2_side) MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_sort_b, 0));
+    if (g2_side) {
+        MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_sort_b, 0));
+        MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_sort_al, 0));
+    }
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_ACC_G1], st));
-    if (trim_rounds) MP_TRY(msm_ba_rounds_needed(g1, 4, cnt, st, &b->ba_g1.round_limit));
-    MP_TRY(msm_accumulate_g1(g1, 4, cnt, ba1, st));
+    if (g2_side && trim_rounds && b->ba_mem_h.p) {
+        // A, B1, L on the third stream (their lists are ready while the witness map still runs), H on the main stream
+        MP_CUDA_TRY(cudaStreamWaitEvent(b->st3, b->ev_sort_b, 0));
+        MP_TRY(msm_ba_rounds_needed(g1, 3, cnt, b->st3, &b->ba_g1.round_limit));
+        MP_TRY(msm_accumulate_g1(g1, 3, cnt, ba1, b->st3));
+        MP_CUDA_TRY(cudaEventRecord(b->ev_acc_abl, b->st3));
+        b->ba_h.round_limit = 0;
+        MP_TRY(msm_ba_rounds_needed(g1 + 3, 1, cnt, st, &b->ba_h.round_limit));
+        MP_TRY(msm_accumulate_g1(g1 + 3, 1, cnt, &b->ba_h, st));
+        MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_acc_abl, 0));
+    } else {
+        if (trim_rounds) MP_TRY(msm_ba_rounds_needed(g1, 4, cnt, st, &b->ba_g1.round_limit));
+        MP_TRY(msm_accumulate_g1(g1, 4, cnt, ba1, st));
+    }
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_REDUCE], st));
     MP_TRY(msm_reduce_heavy_g1(g1, 4, cnt, ba1, st));
     MP_CUDA_TRY(cudaEventRecord(b->ev_heavy, st));  // the next batch of this context may start its kernels now
@@ -720,12 +764,12 @@ static int batch_enqueue(mp_batch* b) {
     c->last_heavy_owner = b;
     MP_TRY(msm_reduce_tail_g1(g1, 4, cnt, ba1, st));
     nvtxRangePop();
-    if (b->overlap) MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_g2, 0));
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_FINISH], st));
     NvtxRange fin("Finish C");
-    k_prove_finish<<<(unsigned)cnt, FINISH_THREADS, 0, st>>>(b->res_g1.as<XYZZ<Fq>>(), b->res_g2.as<XYZZ<Fq2>>(), b->rs.as<uint32_t>(),
-                                                             (uint32_t)cnt, c->glv ? 1 : 0, b->proofs.as<uint8_t>());
+    k_prove_finish<<<(unsigned)cnt, FINISH_THREADS, 0, st>>>(b->res_g1.as<XYZZ<Fq>>(), b->rs.as<uint32_t>(), (uint32_t)cnt, c->glv ? 1 : 0,
+                                                             b->proofs.as<uint8_t>());
     MP_KERNEL_CHECK();
+    if (b->overlap) MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_g2, 0));   // the G2 bytes of the proofs (k_prove_finish_g2 on the other stream)
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_COUNT], st));
     b->launches = kernel_launch_counter() - launches0;
     b->in_flight = true;
@@ -739,6 +783,7 @@ static int batch_finalize(mp_batch* b, float* out_ms) {
     MP_TRY(use_device(b->ctx->device));
     MP_CUDA_TRY(cudaStreamSynchronize(b->st));
     MP_CUDA_TRY(cudaStreamSynchronize(b->st2));
+    MP_CUDA_TRY(cudaStreamSynchronize(b->st3));
     b->in_flight = false;
     float total = 0;
     for (int ph = PH_PREP; ph < PH_COUNT; ph++) MP_CUDA_TRY(cudaEventElapsedTime(&b->phase_ms[ph], b->ev[ph], b->ev[ph + 1]));
@@ -848,6 +893,9 @@ void mp_batch_destroy(mp_batch* b) {
     if (b->ctx) cudaSetDevice(b->ctx->device);
     if (b->st) cudaStreamSynchronize(b->st);
     if (b->st2) cudaStreamSynchronize(b->st2);
+    if (b->st3) cudaStreamSynchronize(b->st3);
+    if (b->ev_sort_al) cudaEventDestroy(b->ev_sort_al);
+    if (b->ev_acc_abl) cudaEventDestroy(b->ev_acc_abl);
     for (auto& e : b->ev)
         if (e) cudaEventDestroy(e);
     if (b->ctx) {
@@ -862,6 +910,7 @@ void mp_batch_destroy(mp_batch* b) {
         if (e) cudaEventDestroy(e);
     if (b->st) cudaStreamDestroy(b->st);
     if (b->st2) cudaStreamDestroy(b->st2);
+    if (b->st3) cudaStreamDestroy(b->st3);
     delete b;
 }
 
