@@ -89,6 +89,11 @@ struct mp_batch {
     // and becomes the H point buffer; the G2 round scratch and the witness-map vectors live inside the G1 round scratch.
     // (Small batches run the G2 MSM on the second stream beside the G1 work and keep everything separate.)
     bool aliased = false;
+    // Outer slabs of the MSM stage (MP_ACC_SLABS = 1, 2 or 4; 2 and 4 are also tried when the device runs out of memory): the
+    // point buffers of the bucket trees - two thirds of a proof's device memory - are sized for capacity / acc_slabs proofs, and
+    // bucket trees + row/column trees run slab after slab over them.  Everything per proof that outlives a slab (sorted lists,
+    // row/column sums, results) keeps its full size; the kernels see a slab through offset pointers.
+    size_t acc_slabs = 1, slab_cap = 0;
     void *p_pb_h = nullptr, *p_pb_b2 = nullptr, *p_abc = nullptr, *p_s1 = nullptr, *p_s2 = nullptr;
     MsmBaWs ba_g1, ba_g2;
     // one or two proofs: the bucket trees of A, B1, L start as soon as their lists are sorted (third stream, beside the witness
@@ -551,10 +556,12 @@ static int ctx_create_impl(const mp_pk_view* pk, const mp_r1cs_view* r1cs, int d
     return MP_OK;
 }
 
-static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch* b) {
+static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, size_t acc_slabs, mp_batch* b) {
     MP_TRY(use_device(c->device));
     b->ctx = c;
     b->capacity = cap;
+    b->acc_slabs = (cap > 16 && msm_use_batched_affine()) ? acc_slabs : 1;
+    b->slab_cap = (cap + b->acc_slabs - 1) / b->acc_slabs;
     size_t free0 = 0, free1 = 0, total_mem = 0;
     MP_CUDA_TRY(cudaMemGetInfo(&free0, &total_mem));
     int prio_least = 0, prio_greatest = 0;
@@ -589,11 +596,12 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch*
     MP_TRY(msm_sort_ws_alloc(b->sort_h, b->gh, cap, b->sort_h_mem));
     const size_t g1w = XYZZ<Fq>::WORDS * 4, g2w = XYZZ<Fq2>::WORDS * 4;
     if (b->use_ba) {
-        MP_TRY(b->pb_a.alloc(cap * b->gz.p_cap * MP_G1_BYTES));
-        MP_TRY(b->pb_b1.alloc(cap * b->gz.p_cap * MP_G1_BYTES));
-        MP_TRY(b->pb_l.alloc(cap * b->gz.p_cap * MP_G1_BYTES));
+        const size_t scap = b->slab_cap;
+        MP_TRY(b->pb_a.alloc(scap * b->gz.p_cap * MP_G1_BYTES));
+        MP_TRY(b->pb_b1.alloc(scap * b->gz.p_cap * MP_G1_BYTES));
+        MP_TRY(b->pb_l.alloc(scap * b->gz.p_cap * MP_G1_BYTES));
         const MsmGeom geoms_g1[4] = {b->gz, b->gz, b->gz, b->gh};
-        const size_t pbh = cap * b->gh.p_cap * MP_G1_BYTES, pbb2 = cap * b->gz.p_cap * MP_G2_BYTES;
+        const size_t pbh = scap * b->gh.p_cap * MP_G1_BYTES, pbb2 = scap * b->gz.p_cap * MP_G2_BYTES;
         const size_t ba1 = msm_ba_ws_bytes(geoms_g1, 4, cap, false), ba2 = msm_ba_ws_bytes(&b->gz, 1, cap, true);
         const size_t wm = (cap * 3 * m * 32 + 255) & ~size_t(255);
         if (b->aliased) {
@@ -657,6 +665,31 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, mp_batch*
     return MP_OK;
 }
 
+// The view of one MSM job for the proofs [s0, ...) of the batch: everything that is indexed by the proof moves by s0, the point
+// buffer of the bucket trees (sized for one slab), the window table and the reduction scratch stay.
+static MsmJob job_slab(const MsmJob& j, size_t s0, size_t point_bytes, size_t xyzz_bytes) {
+    MsmJob o = j;
+    if (s0 == 0) return o;
+    auto shift = [&](MsmSortWs& w, const MsmGeom& g) {
+        w.cnt += s0 * g.n_buckets;
+        w.start += s0 * g.n_buckets;
+        w.fill += s0 * g.n_buckets;
+        w.slot_base += s0 * (g.n_buckets + 1);
+        w.items += s0 * (size_t)g.max_items * 2;
+        w.n_items += s0;
+        w.entries += s0 * (size_t)g.ent_cap;
+        w.heavy += s0 * g.max_heavy;
+        w.n_heavy += s0;
+        w.q += s0 * (size_t)(g.ba_rounds + 1) * (PLAN_THREADS + 1);
+    };
+    shift(o.ws, j.g);
+    shift(o.ws_rc, j.g_rc);
+    o.result = (char*)j.result + s0 * j.g.groups * xyzz_bytes;
+    o.pbuf_rc = (char*)j.pbuf_rc + s0 * (size_t)j.g_rc.p_cap * point_bytes;
+    o.result_rc = (char*)j.result_rc + s0 * j.g_rc.groups * xyzz_bytes;
+    return o;
+}
+
 // Enqueues every kernel of one batch on the batch's streams; returns without synchronising.
 // Main stream: prep -> G2 MSM (B list) -> R1CS + witness map -> A/L/H lists -> G1 MSMs -> finish.  The latency-bound
 // tail of the G2 reduction runs on the second stream beside the witness map and the G1 MSMs.
@@ -686,7 +719,6 @@ static int batch_enqueue(mp_batch* b) {
         {b->gh, b->sort_h, c->tab_h.p, b->part_h.p, res1 + 3 * cnt * g1w, b->red_h.p, b->p_pb_h, b->gh_rc, b->rc_h, b->pbrc_h.p, rrc1 + 6 * cnt * g1w},
     };
     MsmJob g2[1] = {{b->gz, b->sort_b, c->tab_b2.p, b->part_b2.p, b->res_g2.p, b->red_b2.p, b->p_pb_b2, b->gz_rc, b->rc_b2, b->pbrc_b2.p, b->resrc_g2.p}};
-    (void)g2w;
     const MsmBaWs* ba1 = b->use_ba ? &b->ba_g1 : nullptr;
     const MsmBaWs* ba2 = b->use_ba ? &b->ba_g2 : nullptr;
     // ---- G2 MSM over the B list.  Large batches: on the main stream (co-running throughput kernels costs ~5 %), only the
@@ -706,8 +738,13 @@ static int batch_enqueue(mp_batch* b) {
     const bool trim_rounds = b->use_ba && cnt <= 2;
     b->ba_g1.round_limit = b->ba_g2.round_limit = 0;
     if (trim_rounds) MP_TRY(msm_ba_rounds_needed(g2, 1, cnt, sg2, &b->ba_g2.round_limit));
-    MP_TRY(msm_accumulate_g2(g2, 1, cnt, ba2, sg2));
-    MP_TRY(msm_reduce_heavy_g2(g2, 1, cnt, ba2, sg2));
+    const size_t slab = b->acc_slabs > 1 ? b->slab_cap : cnt;   // proofs per pass over the point buffers
+    for (size_t s0 = 0; s0 < cnt; s0 += slab) {
+        const MsmJob js = job_slab(g2[0], s0, MP_G2_BYTES, g2w);
+        const size_t n = std::min(slab, cnt - s0);
+        MP_TRY(msm_accumulate_g2(&js, 1, n, ba2, sg2));
+        MP_TRY(msm_reduce_heavy_g2(&js, 1, n, ba2, sg2));
+    }
     if (b->overlap && !g2_side) {
         MP_CUDA_TRY(cudaEventRecord(b->ev_g2_heavy, st));
         MP_CUDA_TRY(cudaStreamWaitEvent(st_tail, b->ev_g2_heavy, 0));
@@ -755,10 +792,20 @@ static int batch_enqueue(mp_batch* b) {
         MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_acc_abl, 0));
     } else {
         if (trim_rounds) MP_TRY(msm_ba_rounds_needed(g1, 4, cnt, st, &b->ba_g1.round_limit));
-        MP_TRY(msm_accumulate_g1(g1, 4, cnt, ba1, st));
+        if (b->acc_slabs == 1) MP_TRY(msm_accumulate_g1(g1, 4, cnt, ba1, st));
     }
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_REDUCE], st));
-    MP_TRY(msm_reduce_heavy_g1(g1, 4, cnt, ba1, st));
+    if (b->acc_slabs > 1) {   // bucket trees and row/column trees slab after slab (the phase split of the timers ends here)
+        for (size_t s0 = 0; s0 < cnt; s0 += slab) {
+            MsmJob js[4];
+            for (int i = 0; i < 4; i++) js[i] = job_slab(g1[i], s0, MP_G1_BYTES, g1w);
+            const size_t n = std::min(slab, cnt - s0);
+            MP_TRY(msm_accumulate_g1(js, 4, n, ba1, st));
+            MP_TRY(msm_reduce_heavy_g1(js, 4, n, ba1, st));
+        }
+    } else {
+        MP_TRY(msm_reduce_heavy_g1(g1, 4, cnt, ba1, st));
+    }
     MP_CUDA_TRY(cudaEventRecord(b->ev_heavy, st));  // the next batch of this context may start its kernels now
     c->last_heavy = b->ev_heavy;
     c->last_heavy_owner = b;
@@ -877,15 +924,23 @@ int mp_batch_create_ex(mp_ctx* ctx, size_t capacity, int high_priority, mp_batch
         mp::set_error_detail("batch capacity %zu exceeds %d", capacity, MP_MAX_BATCH);
         return MP_ERR_UNSUPPORTED;
     }
-    mp_batch* b = new (std::nothrow) mp_batch();
-    if (!b) return MP_ERR_OOM;
-    int rc = batch_create_impl(ctx, capacity, high_priority, b);
-    if (rc != MP_OK) {
-        mp_batch_destroy(b);
-        return rc;
+    size_t slabs = 1;
+    if (const char* e = getenv("MP_ACC_SLABS")) {
+        const long v = atol(e);
+        slabs = v >= 4 ? 4 : (v >= 2 ? 2 : 1);
     }
-    *out = b;
-    return MP_OK;
+    for (;; slabs *= 2) {   // out of memory: halve the point buffers (two, then four passes over them) before giving up
+        mp_batch* b = new (std::nothrow) mp_batch();
+        if (!b) return MP_ERR_OOM;
+        int rc = batch_create_impl(ctx, capacity, high_priority, slabs, b);
+        if (rc == MP_OK) {
+            *out = b;
+            return MP_OK;
+        }
+        mp_batch_destroy(b);
+        if (rc != MP_ERR_OOM || slabs >= 4 || capacity <= 16) return rc;
+        cudaGetLastError();  // clear the sticky allocation error
+    }
 }
 
 void mp_batch_destroy(mp_batch* b) {

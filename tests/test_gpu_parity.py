@@ -233,6 +233,26 @@ def test_prove_batch_is_chunked(native, monkeypatch):
     ctx.close()
 
 
+@pytest.mark.parametrize("slabs", ["2", "4"])
+def test_prove_batch_with_outer_msm_slabs(native, monkeypatch, slabs):
+    """MP_ACC_SLABS: the point buffers of the bucket trees hold capacity / slabs proofs and the MSM stage runs slab after slab
+    (the out-of-memory fallback of mp_batch_create takes the same path); 45 proofs = uneven slabs, every proof checked."""
+    from manta_rs_b200 import groth16 as g16
+    monkeypatch.setenv("MP_ACC_SLABS", slabs)
+    cs = wl.make_r1cs(3, 150, dist="R")
+    pk, trap = oracle_keygen(cs, wl.sample_trapdoor(15))
+    ctx = g16.ProvingContext.decode(pk)
+    count = 45
+    zs = [wl.make_assignment(cs, 500 + s) for s in range(count)]
+    rng = random.Random(int(slabs))
+    rs = [rng.randrange(C.r) for _ in range(count)]
+    ss = [rng.randrange(C.r) for _ in range(count)]
+    proofs = g16.Groth16.prove_many_with_randomness(ctx, [g16.R1CS.from_workload(cs, z) for z in zs], rs, ss)
+    for i in range(count):
+        assert proofs[i].to_bytes() == trapdoor_proof_bytes(cs, trap, zs[i], rs[i], ss[i]), i
+    ctx.close()
+
+
 def test_prove_batch_more_than_one_device_batch(native):
     """260 proofs through mp_prove_batch: three device batches (128 + 128 + 4) with the default chunk."""
     from manta_rs_b200 import groth16 as g16
