@@ -98,7 +98,7 @@ struct mp_batch {
     MsmBaWs ba_g1, ba_g2;
     // one or two proofs: the bucket trees of A, B1, L start as soon as their lists are sorted (third stream, beside the witness
     // map), those of H follow the witness map on the main stream with a round scratch of their own
-    DevBuf ba_mem_h;
+    DevBuf ba_mem_h, lad;
     MsmBaWs ba_h;
     cudaEvent_t ev_acc_abl = nullptr;
     MsmGeom gz_rc{}, gh_rc{};                                     // row/column stage of the bucket reduction
@@ -432,6 +432,29 @@ __global__ void __launch_bounds__(FINISH_THREADS) k_prove_finish(const XYZZ<Fq>*
         compress_g1(out + 144, c.to_affine());
     }
 }
+// The same in two kernels, for one or two proofs whose A / B1 / L pipeline runs on its own stream ahead of the H pipeline:
+// the ladders (and the bytes of g_a) as soon as the A and B1 results exist, the assembly of g_c once L and H are there.
+// lad: [batch][2] XYZZ (s g_a, r g1_b).
+__global__ void __launch_bounds__(96) k_prove_ladders(const XYZZ<Fq>* __restrict__ res_g1, const uint32_t* __restrict__ rs, uint32_t batch, int glv,
+                                                     uint32_t* lad, uint8_t* proofs) {
+    __shared__ __align__(16) uint32_t slots[2][coop::SLOTS * 12];
+    __shared__ __align__(16) uint32_t scratch[2][16];
+    const uint32_t b = blockIdx.x;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t* r = rs + (size_t)b * 16;
+    const uint32_t* s = r + 8;
+    if (warp == 0) warp_scalar_mul(slots[0], scratch[0], XYZZ<Fq>::load(res_g1 + b), s, glv, lane, lad + (size_t)b * 96);
+    else if (warp == 1) warp_scalar_mul(slots[1], scratch[1], XYZZ<Fq>::load(res_g1 + (size_t)batch + b), r, glv, lane, lad + (size_t)b * 96 + 48);
+    else if (lane == 0) compress_g1(proofs + (size_t)b * MP_PROOF_BYTES, XYZZ<Fq>::load(res_g1 + b).to_affine());
+}
+__global__ void __launch_bounds__(32) k_prove_assemble(const XYZZ<Fq>* __restrict__ res_g1, const uint32_t* __restrict__ lad, uint32_t batch,
+                                                      uint8_t* proofs) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    XYZZ<Fq> c = XYZZ<Fq>::load(lad + (size_t)b * 96).add(XYZZ<Fq>::load(lad + (size_t)b * 96 + 48));
+    c = c.add(XYZZ<Fq>::load(res_g1 + (size_t)2 * batch + b)).add(XYZZ<Fq>::load(res_g1 + (size_t)3 * batch + b));
+    compress_g1(proofs + (size_t)b * MP_PROOF_BYTES + 144, c.to_affine());
+}
 // g2_b -> affine -> the middle 96 bytes of the proof; one thread per proof
 __global__ void __launch_bounds__(32) k_prove_finish_g2(const XYZZ<Fq2>* __restrict__ res_g2, uint32_t batch, uint8_t* proofs) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -625,6 +648,7 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, size_t ac
         if (cap <= 2) {
             MP_TRY(b->ba_mem_h.alloc(msm_ba_ws_bytes(&b->gh, 1, cap, false)));
             msm_ba_ws_bind(b->ba_h, &b->gh, 1, cap, false, b->ba_mem_h.p);
+            MP_TRY(b->lad.alloc(cap * 2 * XYZZ<Fq>::WORDS * 4));
         }
         b->ba_g1.ev_bwd0 = b->ev_dom0;
         b->ba_g1.ev_bwd1 = b->ev_dom1;
@@ -780,16 +804,22 @@ static int batch_enqueue(mp_batch* b) {
         MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_sort_al, 0));
     }
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_ACC_G1], st));
-    if (g2_side && trim_rounds && b->ba_mem_h.p) {
-        // A, B1, L on the third stream (their lists are ready while the witness map still runs), H on the main stream
+    const bool split_abl = g2_side && trim_rounds && b->ba_mem_h.p;
+    if (split_abl) {
+        // A, B1, L on the third stream (their lists are ready while the witness map still runs): bucket trees, reduction and the
+        // two ladders of the finishing step; H on the main stream; they meet in k_prove_assemble
         MP_CUDA_TRY(cudaStreamWaitEvent(b->st3, b->ev_sort_b, 0));
         MP_TRY(msm_ba_rounds_needed(g1, 3, cnt, b->st3, &b->ba_g1.round_limit));
         MP_TRY(msm_accumulate_g1(g1, 3, cnt, ba1, b->st3));
+        MP_TRY(msm_reduce_heavy_g1(g1, 3, cnt, ba1, b->st3));
+        MP_TRY(msm_reduce_tail_g1(g1, 3, cnt, ba1, b->st3));
+        k_prove_ladders<<<(unsigned)cnt, 96, 0, b->st3>>>(b->res_g1.as<XYZZ<Fq>>(), b->rs.as<uint32_t>(), (uint32_t)cnt, c->glv ? 1 : 0,
+                                                         b->lad.as<uint32_t>(), b->proofs.as<uint8_t>());
+        MP_KERNEL_CHECK();
         MP_CUDA_TRY(cudaEventRecord(b->ev_acc_abl, b->st3));
         b->ba_h.round_limit = 0;
         MP_TRY(msm_ba_rounds_needed(g1 + 3, 1, cnt, st, &b->ba_h.round_limit));
         MP_TRY(msm_accumulate_g1(g1 + 3, 1, cnt, &b->ba_h, st));
-        MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_acc_abl, 0));
     } else {
         if (trim_rounds) MP_TRY(msm_ba_rounds_needed(g1, 4, cnt, st, &b->ba_g1.round_limit));
         if (b->acc_slabs == 1) MP_TRY(msm_accumulate_g1(g1, 4, cnt, ba1, st));
@@ -803,18 +833,26 @@ static int batch_enqueue(mp_batch* b) {
             MP_TRY(msm_accumulate_g1(js, 4, n, ba1, st));
             MP_TRY(msm_reduce_heavy_g1(js, 4, n, ba1, st));
         }
+    } else if (split_abl) {
+        MP_TRY(msm_reduce_heavy_g1(g1 + 3, 1, cnt, &b->ba_h, st));
     } else {
         MP_TRY(msm_reduce_heavy_g1(g1, 4, cnt, ba1, st));
     }
     MP_CUDA_TRY(cudaEventRecord(b->ev_heavy, st));  // the next batch of this context may start its kernels now
     c->last_heavy = b->ev_heavy;
     c->last_heavy_owner = b;
-    MP_TRY(msm_reduce_tail_g1(g1, 4, cnt, ba1, st));
+    if (split_abl) MP_TRY(msm_reduce_tail_g1(g1 + 3, 1, cnt, &b->ba_h, st));
+    else MP_TRY(msm_reduce_tail_g1(g1, 4, cnt, ba1, st));
     nvtxRangePop();
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_FINISH], st));
     NvtxRange fin("Finish C");
-    k_prove_finish<<<(unsigned)cnt, FINISH_THREADS, 0, st>>>(b->res_g1.as<XYZZ<Fq>>(), b->rs.as<uint32_t>(), (uint32_t)cnt, c->glv ? 1 : 0,
-                                                             b->proofs.as<uint8_t>());
+    if (split_abl) {
+        MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_acc_abl, 0));
+        k_prove_assemble<<<div_up(cnt, 32), 32, 0, st>>>(b->res_g1.as<XYZZ<Fq>>(), b->lad.as<uint32_t>(), (uint32_t)cnt, b->proofs.as<uint8_t>());
+    } else {
+        k_prove_finish<<<(unsigned)cnt, FINISH_THREADS, 0, st>>>(b->res_g1.as<XYZZ<Fq>>(), b->rs.as<uint32_t>(), (uint32_t)cnt, c->glv ? 1 : 0,
+                                                                 b->proofs.as<uint8_t>());
+    }
     MP_KERNEL_CHECK();
     if (b->overlap) MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_g2, 0));   // the G2 bytes of the proofs (k_prove_finish_g2 on the other stream)
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_COUNT], st));
