@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmantaprover.so")
+LIB_PATH = os.environ.get("MP_LIB_PATH") or os.path.join(_HERE, "libmantaprover.so")   # MP_LIB_PATH: A/B builds of the same library
 
 FR_LIMBS = 4
 G1_BYTES, G2_BYTES, PROOF_BYTES = 96, 192, 192

@@ -20,6 +20,9 @@ namespace mp {
 
 constexpr int NTT_TILE = 2048;      // Fr elements per block tile (64 KiB)
 constexpr int NTT_THREADS = 256;
+#ifndef MP_NTT_BLOCKS
+#define MP_NTT_BLOCKS 3   // resident blocks per SM the register allocation aims at (2 measured no better)
+#endif
 constexpr unsigned NTT_MAX_SUB = 10;  // largest in-SMEM sub-transform (2^10 points)
 constexpr unsigned NTT_MAX_LOG = 26;  // two passes up to 2^20, three up to 2^26 (kzg.rs:43-44 powers; SURVEY.md 5 size axis)
 
@@ -106,7 +109,7 @@ MP_DEV void smem_dif(uint32_t* s, const uint32_t* tws, unsigned lg, unsigned lse
 }
 
 // pass 1 (columns): blockIdx.x = column tile, blockIdx.y = vector
-__global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_cols(NttArgs a) {
+__global__ void __launch_bounds__(NTT_THREADS, MP_NTT_BLOCKS) k_ntt_cols(NttArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const unsigned n1 = 1u << a.l1, n2 = 1u << a.l2;
     const unsigned lC = min(11u - a.l1, a.l2), C = 1u << lC;  // = min(NTT_TILE >> l1, n2)
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_cols(NttArgs a) {
 }
 
 // pass 2 (rows) — also the whole transform when l1 == 0
-__global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_rows(NttArgs a) {
+__global__ void __launch_bounds__(NTT_THREADS, MP_NTT_BLOCKS) k_ntt_rows(NttArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const unsigned n1 = 1u << a.l1, n2 = 1u << a.l2;
     const unsigned lR = min(11u - a.l2, a.l1), R = 1u << lR;  // = min(NTT_TILE >> l2, n1)
