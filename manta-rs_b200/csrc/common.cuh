@@ -42,6 +42,9 @@ uint64_t& kernel_launch_counter();
 // Selects the device and verifies it is an sm_100-class part (no fallback path exists).
 int use_device(int device);
 
+// bytes handed out by DevBuf::alloc on this thread (batch objects report the sum of their buffers from it)
+uint64_t& dev_alloc_counter();
+
 // RAII device buffer (freed on scope exit; never throws)
 struct DevBuf {
     void* p = nullptr;
@@ -55,6 +58,7 @@ struct DevBuf {
         if (n == 0) n = 16;
         MP_CUDA_TRY(cudaMalloc(&p, n));
         bytes = n;
+        dev_alloc_counter() += n;
         return MP_OK;
     }
     void release() {

@@ -12,6 +12,11 @@ uint64_t& kernel_launch_counter() {
     return n;
 }
 
+uint64_t& dev_alloc_counter() {
+    static thread_local uint64_t n = 0;
+    return n;
+}
+
 void set_error_detail(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);

@@ -18,7 +18,7 @@
 namespace mp {
 
 constexpr int MSM_CLASSES = 64;        // length classes used to order work items (longest first)
-constexpr int MSM_MAX_JOBS = 4;        // MSMs handled by one accumulate / reduce launch
+constexpr int MSM_MAX_JOBS = 6;        // MSMs handled by one accumulate / reduce launch
 constexpr int MSM_HEAVY_SEGS = 33;     // buckets with this many slices or more are folded by a whole warp
 constexpr int PLAN_THREADS = 1024;     // threads of the per-list plan block = bucket chunks of the pair index
 constexpr int BA_BLK = 128;            // threads per block of the batched-affine round kernels
@@ -103,8 +103,20 @@ struct MsmBaWs {
     void* tot = nullptr;       // F per thread: product of its denominators, then its inverse
     void* pre2 = nullptr;      // F per thread: second-level prefix products
     size_t cap_pairs = 0, cap_threads = 0;  // slots behind prefix/desc and tot/pre2 (sized for every count <= capacity)
+    // Software pipeline over the slabs of a tree level (batches of more than 32 vectors): a SECOND scratch set of the same size,
+    // so that the forward pass of slab i+1 and the backward pass of slab i-1 run while the latency-bound inversion kernel of
+    // slab i sits on a high-priority side stream.  n_sets == 1 or no side streams: one launch triple after the other.
+    int n_sets = 1;
+    void* prefix_b = nullptr;
+    uint32_t* desc_b = nullptr;
+    void* tot_b = nullptr;
+    void* pre2_b = nullptr;
+    cudaStream_t mid_st[2] = {nullptr, nullptr};                               // side streams of k_ba_mid (owned by the caller)
+    cudaEvent_t ev_fwd[2] = {nullptr, nullptr}, ev_mid[2] = {nullptr, nullptr};  // fwd done -> mid may start; mid done -> bwd may start
     mutable size_t dom_count = 0;           // vectors covered by the launch the ev_bwd0/1 events bracket (first slab of level 1)
     int round_limit = 0;                    // > 0: launch only this many tree levels (msm_ba_rounds_needed), 0: every provisioned level
+    // (a limit below the populated levels leaves up to 2^(populated - limit) points per bucket; the latency path of the bucket
+    //  reduction, reduce_small, adds those while it walks the buckets - see msm_ba_trim_levels)
     // optional: recorded around the round-1 k_ba_bwd launch of the bucket trees (the dominant kernel of a proof)
     cudaEvent_t ev_bwd0 = nullptr, ev_bwd1 = nullptr;
 };
@@ -114,6 +126,11 @@ size_t msm_ba_slab(size_t batch, bool g2);   // vectors the round scratch of a b
 // host-only: {pairs, threads} a live `count` needs and {pairs, threads} a workspace sized for `cap` provides
 void msm_ba_ws_demand(const MsmGeom* geoms, int n_jobs, size_t cap, size_t count, uint64_t out[4]);
 int msm_ba_rounds_needed(const MsmJob* jobs, int n_jobs, size_t batch, cudaStream_t st, int* out_rounds);
+// Tree levels a latency-bound launch (<= 2 vectors) leaves to the reduction (MP_BA_TRIM_LEVELS, default 0): every level costs a
+// serial ~85 us inversion, the <= 2^trim leftover points of a bucket cost the reduction's lanes serial mixed additions.
+// Measured on the B200 (profiles/r02q_*): 4.89 / 5.23 / 5.62 / 7.64 ms per proof for 0 / 1 / 2 / 3 levels - the additions cost
+// more than the levels they replace - so nothing is trimmed by default.
+int msm_ba_trim_levels();
 // ba == nullptr selects the XYZZ accumulation (jobs[].partial), otherwise batched affine (jobs[].pbuf)
 int msm_accumulate_g1(const MsmJob* jobs, int n_jobs, size_t batch, const MsmBaWs* ba, cudaStream_t st);
 int msm_accumulate_g2(const MsmJob* jobs, int n_jobs, size_t batch, const MsmBaWs* ba, cudaStream_t st);

@@ -78,6 +78,9 @@ struct mp_batch {
     cudaEvent_t ev_sort_al = nullptr;
     cudaEvent_t ev_g2_heavy = nullptr, ev_g2 = nullptr, ev_heavy = nullptr, ev_tail_fork = nullptr, ev_sort_b = nullptr;
     cudaEvent_t ev_dom0 = nullptr, ev_dom1 = nullptr;  // around the dominant kernel (round-1 k_ba_bwd<Fq> of the G1 bucket trees)
+    // slab pipeline of the tree levels (msm_impl.inc accumulate_ba): two highest-priority side streams for the inversion kernels
+    cudaStream_t st_mid[2] = {nullptr, nullptr};
+    cudaEvent_t ev_pipe[4] = {nullptr, nullptr, nullptr, nullptr};
     bool overlap = true;
     DevBuf z_canon, z_mont, rs, abc, s1, s2, h_canon;
     DevBuf sort_a_mem, sort_b_mem, sort_l_mem, sort_h_mem;
@@ -100,6 +103,12 @@ struct mp_batch {
     // map), those of H follow the witness map on the main stream with a round scratch of their own
     DevBuf ba_mem_h, lad;
     MsmBaWs ba_h;
+    // one or two proofs, key inside the prime-order subgroup: s * g_a and r * g1_b are computed as two more MSMs over the A and
+    // B1 tables with the scalar vectors s z' and r z' (same launches as A, B1, L: no depth added) instead of two 128-step ladders
+    // behind the A / B1 results.  zx: [3][count] rows of zlen scalars: r z' | z' | s z' (the A and B lists are sorted as 2 * count
+    // vectors: one sort call each).
+    DevBuf zx, red_sa, red_rb, ba_mem_abl;
+    MsmBaWs ba_abl;
     cudaEvent_t ev_acc_abl = nullptr;
     MsmGeom gz_rc{}, gh_rc{};                                     // row/column stage of the bucket reduction
     DevBuf rc_a_mem, rc_b_mem, rc_b2_mem, rc_l_mem, rc_h_mem, pbrc_a, pbrc_b1, pbrc_l, pbrc_h, pbrc_b2, resrc_g1, resrc_g2;
@@ -150,6 +159,19 @@ __global__ void k_prove_prep(uint32_t* z_canon, uint32_t* z_mont, const uint32_t
         one.l[0] = 1;
         one.store(zc + (size_t)(n + 3) * 8);
     }
+}
+
+// zx rows: [r z' | z' | s z'], `cnt` rows each (z' = the extended scalar vector k_prove_prep completed): MSM_A(s z') = s g_a and
+// MSM_B1(r z') = r g1_b when every table point has order r.  mont(r) * v is the canonical product for canonical v.
+__global__ void k_prove_scale(const uint32_t* __restrict__ z_canon, const uint32_t* __restrict__ rs, uint32_t zlen, uint32_t cnt, uint32_t* zx) {
+    const uint32_t b = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= zlen) return;
+    const Fr v = Fr::load(z_canon + ((size_t)b * zlen + i) * 8);
+    const Fr r = Fr::load(rs + (size_t)b * 16).to_mont(), s = Fr::load(rs + (size_t)b * 16 + 8).to_mont();
+    (r * v).store(zx + ((size_t)b * zlen + i) * 8);
+    v.store(zx + ((size_t)(cnt + b) * zlen + i) * 8);
+    (s * v).store(zx + ((size_t)(2 * cnt + b) * zlen + i) * 8);
 }
 
 template <class F>
@@ -455,6 +477,20 @@ __global__ void __launch_bounds__(32) k_prove_assemble(const XYZZ<Fq>* __restric
     c = c.add(XYZZ<Fq>::load(res_g1 + (size_t)2 * batch + b)).add(XYZZ<Fq>::load(res_g1 + (size_t)3 * batch + b));
     compress_g1(proofs + (size_t)b * MP_PROOF_BYTES + 144, c.to_affine());
 }
+// The finishing step when s g_a and r g1_b came out of MSMs (res_g1: [6][batch] XYZZ: A, B1, L, H, s g_a, r g1_b): one block
+// per proof; warp 0 writes the bytes of g_a, warp 1 those of g_c = s g_a + r g1_b + L + H.
+__global__ void __launch_bounds__(64) k_prove_assemble_msm(const XYZZ<Fq>* __restrict__ res_g1, uint32_t batch, uint8_t* proofs) {
+    const uint32_t b = blockIdx.x;
+    if (threadIdx.x & 31) return;
+    uint8_t* out = proofs + (size_t)b * MP_PROOF_BYTES;
+    if (threadIdx.x == 0) {
+        compress_g1(out, XYZZ<Fq>::load(res_g1 + b).to_affine());
+    } else {
+        XYZZ<Fq> c = XYZZ<Fq>::load(res_g1 + (size_t)4 * batch + b).add(XYZZ<Fq>::load(res_g1 + (size_t)5 * batch + b));
+        c = c.add(XYZZ<Fq>::load(res_g1 + (size_t)2 * batch + b)).add(XYZZ<Fq>::load(res_g1 + (size_t)3 * batch + b));
+        compress_g1(out + 144, c.to_affine());
+    }
+}
 // g2_b -> affine -> the middle 96 bytes of the proof; one thread per proof
 __global__ void __launch_bounds__(32) k_prove_finish_g2(const XYZZ<Fq2>* __restrict__ res_g2, uint32_t batch, uint8_t* proofs) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -585,8 +621,7 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, size_t ac
     b->capacity = cap;
     b->acc_slabs = (cap > 16 && msm_use_batched_affine()) ? acc_slabs : 1;
     b->slab_cap = (cap + b->acc_slabs - 1) / b->acc_slabs;
-    size_t free0 = 0, free1 = 0, total_mem = 0;
-    MP_CUDA_TRY(cudaMemGetInfo(&free0, &total_mem));
+    const uint64_t alloc0 = dev_alloc_counter();
     int prio_least = 0, prio_greatest = 0;
     MP_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
     const int prio = high_priority ? prio_greatest : prio_least;
@@ -613,15 +648,16 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, size_t ac
     MP_TRY(b->h_canon.alloc(cap * m * 32));
     b->gz = msm_geom(PROVE_C, 1, c->zlen, c->zlen, cap * 2);  // G1 launches carry 4 jobs, the G2 launch one
     b->gh = msm_geom(PROVE_C, 1, (uint32_t)c->m, (uint32_t)c->m, cap * 2);
-    MP_TRY(msm_sort_ws_alloc(b->sort_a, b->gz, cap, b->sort_a_mem));
-    MP_TRY(msm_sort_ws_alloc(b->sort_b, b->gz, cap, b->sort_b_mem));
+    const bool ext = msm_use_batched_affine() && cap <= 2;   // the A and B lists also carry the scaled vectors (see `zx`)
+    MP_TRY(msm_sort_ws_alloc(b->sort_a, b->gz, ext ? 2 * cap : cap, b->sort_a_mem));
+    MP_TRY(msm_sort_ws_alloc(b->sort_b, b->gz, ext ? 2 * cap : cap, b->sort_b_mem));
     MP_TRY(msm_sort_ws_alloc(b->sort_l, b->gz, cap, b->sort_l_mem));
     MP_TRY(msm_sort_ws_alloc(b->sort_h, b->gh, cap, b->sort_h_mem));
     const size_t g1w = XYZZ<Fq>::WORDS * 4, g2w = XYZZ<Fq2>::WORDS * 4;
     if (b->use_ba) {
         const size_t scap = b->slab_cap;
-        MP_TRY(b->pb_a.alloc(scap * b->gz.p_cap * MP_G1_BYTES));
-        MP_TRY(b->pb_b1.alloc(scap * b->gz.p_cap * MP_G1_BYTES));
+        MP_TRY(b->pb_a.alloc((ext ? 2 : 1) * scap * b->gz.p_cap * MP_G1_BYTES));
+        MP_TRY(b->pb_b1.alloc((ext ? 2 : 1) * scap * b->gz.p_cap * MP_G1_BYTES));
         MP_TRY(b->pb_l.alloc(scap * b->gz.p_cap * MP_G1_BYTES));
         const MsmGeom geoms_g1[4] = {b->gz, b->gz, b->gz, b->gh};
         const size_t pbh = scap * b->gh.p_cap * MP_G1_BYTES, pbb2 = scap * b->gz.p_cap * MP_G2_BYTES;
@@ -649,9 +685,24 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, size_t ac
             MP_TRY(b->ba_mem_h.alloc(msm_ba_ws_bytes(&b->gh, 1, cap, false)));
             msm_ba_ws_bind(b->ba_h, &b->gh, 1, cap, false, b->ba_mem_h.p);
             MP_TRY(b->lad.alloc(cap * 2 * XYZZ<Fq>::WORDS * 4));
+            const MsmGeom geoms_abl[5] = {b->gz, b->gz, b->gz, b->gz, b->gz};
+            MP_TRY(b->ba_mem_abl.alloc(msm_ba_ws_bytes(geoms_abl, 5, cap, false)));
+            msm_ba_ws_bind(b->ba_abl, geoms_abl, 5, cap, false, b->ba_mem_abl.p);
+            MP_TRY(b->zx.alloc(3 * cap * c->zlen * 32));
+            MP_TRY(b->red_sa.alloc(msm_reduce_scratch_bytes(b->gz, cap, false)));
+            MP_TRY(b->red_rb.alloc(msm_reduce_scratch_bytes(b->gz, cap, false)));
         }
         b->ba_g1.ev_bwd0 = b->ev_dom0;
         b->ba_g1.ev_bwd1 = b->ev_dom1;
+        if (b->ba_g1.n_sets == 2 || b->ba_g2.n_sets == 2) {
+            for (auto& s : b->st_mid) MP_CUDA_TRY(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_greatest));
+            for (auto& e : b->ev_pipe) MP_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            for (MsmBaWs* w : {&b->ba_g1, &b->ba_g2}) {   // both run on the main stream of a large batch, one after the other
+                w->mid_st[0] = b->st_mid[0]; w->mid_st[1] = b->st_mid[1];
+                w->ev_fwd[0] = b->ev_pipe[0]; w->ev_fwd[1] = b->ev_pipe[1];
+                w->ev_mid[0] = b->ev_pipe[2]; w->ev_mid[1] = b->ev_pipe[3];
+            }
+        }
         b->gz_rc = msm_geom_rc(b->gz);
         b->gh_rc = msm_geom_rc(b->gh);
         MP_TRY(msm_sort_ws_alloc(b->rc_a, b->gz_rc, cap, b->rc_a_mem));
@@ -673,7 +724,7 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, size_t ac
         MP_TRY(b->part_h.alloc(cap * b->gh.max_items * g1w));
         MP_TRY(b->part_b2.alloc(cap * b->gz.max_items * g2w));
     }
-    MP_TRY(b->res_g1.alloc(4 * cap * g1w));
+    MP_TRY(b->res_g1.alloc(6 * cap * g1w));   // A, B1, L, H (+ s g_a, r g1_b as MSMs for one or two proofs)
     MP_TRY(b->res_g2.alloc(cap * g2w));
     MP_TRY(b->red_a.alloc(msm_reduce_scratch_bytes(b->gz, cap, false)));
     MP_TRY(b->red_b1.alloc(msm_reduce_scratch_bytes(b->gz, cap, false)));
@@ -684,34 +735,177 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, size_t ac
     MP_TRY(b->bad_dev.alloc(4));
     MP_CUDA_TRY(cudaHostAlloc((void**)&b->bad_host, 4, cudaHostAllocDefault));
     *b->bad_host = 0;
-    MP_CUDA_TRY(cudaMemGetInfo(&free1, &total_mem));
-    b->device_bytes = free0 > free1 ? free0 - free1 : 0;
+    b->device_bytes = dev_alloc_counter() - alloc0;   // every per-proof buffer is a DevBuf allocated above
     return MP_OK;
 }
 
 // The view of one MSM job for the proofs [s0, ...) of the batch: everything that is indexed by the proof moves by s0, the point
 // buffer of the bucket trees (sized for one slab), the window table and the reduction scratch stay.
+static void shift_sort_ws(MsmSortWs& w, const MsmGeom& g, size_t s0) {
+    w.cnt += s0 * g.n_buckets;
+    w.start += s0 * g.n_buckets;
+    w.fill += s0 * g.n_buckets;
+    w.slot_base += s0 * (g.n_buckets + 1);
+    w.items += s0 * (size_t)g.max_items * 2;
+    w.n_items += s0;
+    w.entries += s0 * (size_t)g.ent_cap;
+    w.heavy += s0 * g.max_heavy;
+    w.n_heavy += s0;
+    w.q += s0 * (size_t)(g.ba_rounds + 1) * (PLAN_THREADS + 1);
+}
+// The same job over the vectors [s0, ...) of its sorted list only (everything else - buffers, results - stays).
+static MsmJob job_list_view(const MsmJob& j, size_t s0) {
+    MsmJob o = j;
+    shift_sort_ws(o.ws, j.g, s0);
+    return o;
+}
 static MsmJob job_slab(const MsmJob& j, size_t s0, size_t point_bytes, size_t xyzz_bytes) {
     MsmJob o = j;
     if (s0 == 0) return o;
-    auto shift = [&](MsmSortWs& w, const MsmGeom& g) {
-        w.cnt += s0 * g.n_buckets;
-        w.start += s0 * g.n_buckets;
-        w.fill += s0 * g.n_buckets;
-        w.slot_base += s0 * (g.n_buckets + 1);
-        w.items += s0 * (size_t)g.max_items * 2;
-        w.n_items += s0;
-        w.entries += s0 * (size_t)g.ent_cap;
-        w.heavy += s0 * g.max_heavy;
-        w.n_heavy += s0;
-        w.q += s0 * (size_t)(g.ba_rounds + 1) * (PLAN_THREADS + 1);
-    };
-    shift(o.ws, j.g);
-    shift(o.ws_rc, j.g_rc);
+    shift_sort_ws(o.ws, j.g, s0);
+    shift_sort_ws(o.ws_rc, j.g_rc, s0);
     o.result = (char*)j.result + s0 * j.g.groups * xyzz_bytes;
     o.pbuf_rc = (char*)j.pbuf_rc + s0 * (size_t)j.g_rc.p_cap * point_bytes;
     o.result_rc = (char*)j.result_rc + s0 * j.g_rc.groups * xyzz_bytes;
     return o;
+}
+
+// Small batches (<= 16 proofs with separate buffers) leave the GPU mostly idle and are bound by the serial steps of three chains,
+// each on its own stream:
+//   second stream: B list -> G2 bucket trees -> G2 reduction -> G2 bytes
+//   third stream : A and L lists (-> for one or two proofs: bucket trees and reduction of A, B1, L [+ the s g_a and r g1_b MSMs])
+//   main stream  : witness map -> H list -> H trees -> H reduction -> assembly of g_c
+// Everything that needs no read-back (the sorts, the witness map) is enqueued FIRST: the host blocks in msm_ba_rounds_needed
+// (one or two proofs: how many tree levels are populated) and the chains behind those read-backs start in the order their
+// lists become ready.
+static int batch_enqueue_small(mp_batch* b, MsmJob* g1, MsmJob* g2, uint64_t launches0) {
+    mp_ctx* c = b->ctx;
+    const size_t cnt = b->count, cap = b->capacity;
+    cudaStream_t st = b->st, sg2 = b->st2, s3 = b->st3;
+    const size_t g1w = XYZZ<Fq>::WORDS * 4;
+    const MsmBaWs* ba1 = b->use_ba ? &b->ba_g1 : nullptr;
+    const MsmBaWs* ba2 = b->use_ba ? &b->ba_g2 : nullptr;
+    const bool trim_rounds = b->use_ba && cnt <= 2;
+    const bool split_abl = trim_rounds && b->ba_mem_h.p;
+    // MP_LADDERS_AS_MSM=1: s g_a and r g1_b as two more MSM jobs (valid when every A / B1 table point has order r - the GLV
+    // condition).  Measured on the B200 (profiles/r02q_*): 4.89 ms per proof against 4.74 with the ladders - the G2 chain is
+    // the critical path of a single proof, and the extra MSM work slows it down more than the shorter A / B1 / L chain helps.
+    bool ext = false;
+    if (const char* e = getenv("MP_LADDERS_AS_MSM")) ext = e[0] == '1' && split_abl && c->glv && b->zx.p;
+    const size_t row = (size_t)c->zlen * 8;   // words per scalar vector
+    const uint32_t* zc = b->z_canon.as<uint32_t>();
+    const uint32_t* zx = b->zx.as<uint32_t>();
+    b->ba_g1.round_limit = b->ba_g2.round_limit = b->ba_h.round_limit = b->ba_abl.round_limit = 0;
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_G2], st));
+    if (ext) {
+        k_prove_scale<<<dim3(div_up(c->zlen, 256), (unsigned)cnt), 256, 0, st>>>(zc, b->rs.as<uint32_t>(), c->zlen, (uint32_t)cnt, b->zx.as<uint32_t>());
+        MP_KERNEL_CHECK();
+    }
+    MP_CUDA_TRY(cudaEventRecord(b->ev_tail_fork, st));  // z' complete
+    MP_CUDA_TRY(cudaStreamWaitEvent(sg2, b->ev_tail_fork, 0));
+    MP_CUDA_TRY(cudaStreamWaitEvent(s3, b->ev_tail_fork, 0));
+    // ---- lists.  ext: the B list is sorted as 2 cnt vectors (r z' | z'), the A list as (z' | s z')
+    nvtxRangePushA("Compute B in G2");
+    if (ext) MP_TRY(msm_sort(b->gz, zx, row, 2 * cnt, b->sort_b, c->valid_b.as<uint32_t>(), sg2));
+    else MP_TRY(msm_sort(b->gz, zc, row, cnt, b->sort_b, c->valid_b.as<uint32_t>(), sg2));
+    MP_CUDA_TRY(cudaEventRecord(b->ev_sort_b, sg2));  // the B1 job of the G1 launch reads the B list
+    if (ext) MP_TRY(msm_sort(b->gz, zx + cnt * row, row, 2 * cnt, b->sort_a, c->valid_a.as<uint32_t>(), s3));
+    else MP_TRY(msm_sort(b->gz, zc, row, cnt, b->sort_a, c->valid_a.as<uint32_t>(), s3));
+    MP_TRY(msm_sort(b->gz, zc, row, cnt, b->sort_l, c->valid_l.as<uint32_t>(), s3));
+    MP_CUDA_TRY(cudaEventRecord(b->ev_sort_al, s3));
+    nvtxRangePop();
+    // ---- witness map and H list
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_WITNESS_MAP], st));
+    nvtxRangePushA("R1CS to QAP witness map");
+    if (!b->abc_supplied) MP_TRY(r1cs_eval(c->r1cs, b->z_mont.p, c->zlen, cnt, c->m, b->p_abc, st));
+    MP_TRY(witness_map_run(c->dom, b->p_abc, b->p_s1, b->p_s2, cnt, b->h_canon.p, c->m, st));
+    nvtxRangePop();
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_SORT], st));
+    MP_TRY(msm_sort(b->gh, b->h_canon.as<uint32_t>(), (size_t)c->m * 8, cnt, b->sort_h, c->valid_h.as<uint32_t>(), st));
+    // ---- G2 chain
+    {
+        nvtxRangePushA("Compute B in G2");
+        MsmJob jg2 = ext ? job_list_view(g2[0], cnt) : g2[0];
+        if (trim_rounds) MP_TRY(msm_ba_rounds_needed(&jg2, 1, cnt, sg2, &b->ba_g2.round_limit));
+        MP_TRY(msm_accumulate_g2(&jg2, 1, cnt, ba2, sg2));
+        MP_TRY(msm_reduce_heavy_g2(&jg2, 1, cnt, ba2, sg2));
+        MP_TRY(msm_reduce_tail_g2(&jg2, 1, cnt, ba2, sg2));
+        k_prove_finish_g2<<<div_up(cnt, 32), 32, 0, sg2>>>(b->res_g2.as<XYZZ<Fq2>>(), (uint32_t)cnt, b->proofs.as<uint8_t>());
+        MP_KERNEL_CHECK();
+        MP_CUDA_TRY(cudaEventRecord(b->ev_g2, sg2));
+        nvtxRangePop();
+    }
+    // ---- A, B1, L chain of one or two proofs
+    nvtxRangePushA("Compute A, Compute B in G1, Compute C (H and L queries)");
+    if (split_abl) {
+        MP_CUDA_TRY(cudaStreamWaitEvent(s3, b->ev_sort_b, 0));
+        MsmJob abl[5];
+        int n_abl = 3;
+        MsmBaWs* w = &b->ba_g1;
+        abl[0] = g1[0];
+        abl[1] = ext ? job_list_view(g1[1], cnt) : g1[1];
+        abl[2] = g1[2];
+        if (ext) {
+            char* res1 = b->res_g1.as<char>();
+            abl[3] = job_list_view(g1[0], cnt);   // s z' over the A table
+            abl[3].pbuf = b->pb_a.as<char>() + cap * b->gz.p_cap * MP_G1_BYTES;
+            abl[3].result = res1 + 4 * cnt * g1w;
+            abl[3].scratch = b->red_sa.p;
+            abl[4] = g1[1];                       // r z' over the B1 table: the first half of the B list
+            abl[4].pbuf = b->pb_b1.as<char>() + cap * b->gz.p_cap * MP_G1_BYTES;
+            abl[4].result = res1 + 5 * cnt * g1w;
+            abl[4].scratch = b->red_rb.p;
+            n_abl = 5;
+            w = &b->ba_abl;
+        }
+        MP_TRY(msm_ba_rounds_needed(abl, n_abl, cnt, s3, &w->round_limit));
+        MP_TRY(msm_accumulate_g1(abl, n_abl, cnt, w, s3));
+        MP_TRY(msm_reduce_heavy_g1(abl, n_abl, cnt, w, s3));
+        MP_TRY(msm_reduce_tail_g1(abl, n_abl, cnt, w, s3));
+        if (!ext) {
+            k_prove_ladders<<<(unsigned)cnt, 96, 0, s3>>>(b->res_g1.as<XYZZ<Fq>>(), b->rs.as<uint32_t>(), (uint32_t)cnt, c->glv ? 1 : 0,
+                                                         b->lad.as<uint32_t>(), b->proofs.as<uint8_t>());
+            MP_KERNEL_CHECK();
+        }
+        MP_CUDA_TRY(cudaEventRecord(b->ev_acc_abl, s3));
+    } else {
+        MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_sort_b, 0));
+        MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_sort_al, 0));
+    }
+    // ---- H chain (or all four G1 MSMs) on the main stream
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_ACC_G1], st));
+    if (split_abl) {
+        MP_TRY(msm_ba_rounds_needed(g1 + 3, 1, cnt, st, &b->ba_h.round_limit));
+        MP_TRY(msm_accumulate_g1(g1 + 3, 1, cnt, &b->ba_h, st));
+    } else {
+        if (trim_rounds) MP_TRY(msm_ba_rounds_needed(g1, 4, cnt, st, &b->ba_g1.round_limit));
+        MP_TRY(msm_accumulate_g1(g1, 4, cnt, ba1, st));
+    }
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_REDUCE], st));
+    if (split_abl) MP_TRY(msm_reduce_heavy_g1(g1 + 3, 1, cnt, &b->ba_h, st));
+    else MP_TRY(msm_reduce_heavy_g1(g1, 4, cnt, ba1, st));
+    MP_CUDA_TRY(cudaEventRecord(b->ev_heavy, st));  // the next batch of this context may start its kernels now
+    c->last_heavy = b->ev_heavy;
+    c->last_heavy_owner = b;
+    if (split_abl) MP_TRY(msm_reduce_tail_g1(g1 + 3, 1, cnt, &b->ba_h, st));
+    else MP_TRY(msm_reduce_tail_g1(g1, 4, cnt, ba1, st));
+    nvtxRangePop();
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_FINISH], st));
+    NvtxRange fin("Finish C");
+    if (split_abl) {
+        MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_acc_abl, 0));
+        if (ext) k_prove_assemble_msm<<<(unsigned)cnt, 64, 0, st>>>(b->res_g1.as<XYZZ<Fq>>(), (uint32_t)cnt, b->proofs.as<uint8_t>());
+        else k_prove_assemble<<<div_up(cnt, 32), 32, 0, st>>>(b->res_g1.as<XYZZ<Fq>>(), b->lad.as<uint32_t>(), (uint32_t)cnt, b->proofs.as<uint8_t>());
+    } else {
+        k_prove_finish<<<(unsigned)cnt, FINISH_THREADS, 0, st>>>(b->res_g1.as<XYZZ<Fq>>(), b->rs.as<uint32_t>(), (uint32_t)cnt, c->glv ? 1 : 0,
+                                                                 b->proofs.as<uint8_t>());
+    }
+    MP_KERNEL_CHECK();
+    MP_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_g2, 0));   // the G2 bytes of the proofs (k_prove_finish_g2 on the second stream)
+    MP_CUDA_TRY(cudaEventRecord(b->ev[PH_COUNT], st));
+    b->launches = kernel_launch_counter() - launches0;
+    b->in_flight = true;
+    return MP_OK;
 }
 
 // Enqueues every kernel of one batch on the batch's streams; returns without synchronising.
@@ -749,6 +943,10 @@ static int batch_enqueue(mp_batch* b) {
     // latency-bound tail of its reduction on the second stream.  Small batches leave the GPU mostly idle and are bound by the
     // per-level latencies of the trees: the whole G2 MSM then runs on the second stream beside the witness map and the G1 MSMs.
     const bool g2_side = b->overlap && cnt <= 16 && !b->aliased;
+    if (g2_side) {
+        const char* e = getenv("MP_SMALL_PATH_OLD");   // A/B hook: the first form of the small-batch path, below
+        if (!(e && e[0] == '1')) return batch_enqueue_small(b, g1, g2, launches0);
+    }
     cudaStream_t sg2 = g2_side ? b->st2 : st;
     MP_CUDA_TRY(cudaEventRecord(b->ev[PH_G2], st));
     nvtxRangePushA("Compute B in G2");
@@ -1001,6 +1199,10 @@ void mp_batch_destroy(mp_batch* b) {
     if (b->bad_host) cudaFreeHost(b->bad_host);
     for (cudaEvent_t e : {b->ev_g2_heavy, b->ev_g2, b->ev_heavy, b->ev_tail_fork, b->ev_sort_b, b->ev_dom0, b->ev_dom1})
         if (e) cudaEventDestroy(e);
+    for (auto e : b->ev_pipe)
+        if (e) cudaEventDestroy(e);
+    for (auto st : b->st_mid)
+        if (st) cudaStreamDestroy(st);
     if (b->st) cudaStreamDestroy(b->st);
     if (b->st2) cudaStreamDestroy(b->st2);
     if (b->st3) cudaStreamDestroy(b->st3);

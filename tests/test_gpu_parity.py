@@ -253,6 +253,29 @@ def test_prove_batch_with_outer_msm_slabs(native, monkeypatch, slabs):
     ctx.close()
 
 
+@pytest.mark.parametrize("pipe,div,count", [("1", "4", 45), ("1", "2", 70), ("1", "16", 130), ("0", "2", 45)])
+def test_prove_batch_with_pipelined_tree_levels(native, monkeypatch, pipe, div, count):
+    """Batches of more than 32 proofs run every tree level as a software pipeline over slabs of proofs (two round-scratch sets,
+    the inversion kernels on side streams); MP_BA_PIPE_MIN_LOG2=0 forces the slab cut on a small circuit.  Uneven slabs, the
+    drained and the un-pipelined forms, every proof checked against the closed form."""
+    from manta_rs_b200 import groth16 as g16
+    monkeypatch.setenv("MP_BA_PIPE", pipe)
+    monkeypatch.setenv("MP_BA_SLAB_DIV", div)
+    monkeypatch.setenv("MP_BA_PIPE_MIN_LOG2", "0")
+    monkeypatch.setenv("MP_PROVE_BATCH_CHUNK", "256")
+    cs = wl.make_r1cs(3, 170, dist="R")
+    pk, trap = oracle_keygen(cs, wl.sample_trapdoor(21))
+    ctx = g16.ProvingContext.decode(pk)
+    zs = [wl.make_assignment(cs, 700 + s) for s in range(count)]
+    rng = random.Random(count)
+    rs = [rng.randrange(C.r) for _ in range(count)]
+    ss = [rng.randrange(C.r) for _ in range(count)]
+    proofs = g16.Groth16.prove_many_with_randomness(ctx, [g16.R1CS.from_workload(cs, z) for z in zs], rs, ss)
+    for i in range(count):
+        assert proofs[i].to_bytes() == trapdoor_proof_bytes(cs, trap, zs[i], rs[i], ss[i]), i
+    ctx.close()
+
+
 def test_prove_batch_more_than_one_device_batch(native):
     """260 proofs through mp_prove_batch: three device batches (128 + 128 + 4) with the default chunk."""
     from manta_rs_b200 import groth16 as g16
@@ -609,6 +632,46 @@ def test_msm_closed_form_large(native):
     out = ctypes.create_string_buffer(96)
     _chk(native, native.lib().mp_msm_g1(0, bases, native.pack_scalars(sc), n, out, None))
     assert out.raw == cref.fixed_base(1, [sum(k * s for k, s in zip(ks, sc)) % C.r])
+
+
+@pytest.mark.parametrize("env", [{}, {"MP_LADDERS_AS_MSM": "1"}, {"MP_LADDERS_AS_MSM": "1", "MP_BA_TRIM_LEVELS": "2"},
+                                 {"MP_BA_TRIM_LEVELS": "1"}, {"MP_BA_TRIM_LEVELS": "4"}, {"MP_SMALL_PATH_OLD": "1"},
+                                 {"MP_LADDERS_AS_MSM": "1", "MP_NO_GLV": "1"}])
+def test_latency_path_of_one_and_two_proofs(native, monkeypatch, env):
+    """One or two proofs (three chains on three streams).  The measured alternatives behind the environment switches give the
+    same bytes: s g_a and r g1_b as two more MSM jobs over the A / B1 tables (MP_LADDERS_AS_MSM: scaled scalar vectors, lists
+    sorted as 2 x count vectors) instead of ladders, bucket trees that stop MP_BA_TRIM_LEVELS levels early (the reduction adds
+    the leftover points of a bucket), the first form of the enqueue order.  Capacity-2 batch with 2 and with 1 proof,
+    serialised mode, special r / s."""
+    from manta_rs_b200 import groth16 as g16
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    lib = native.lib()
+    cs = wl.make_r1cs(3, 900, dist="R")
+    pk, trap = oracle_keygen(cs, wl.sample_trapdoor(31))
+    ctx = g16.ProvingContext.decode(pk)
+    zs = [wl.make_assignment(cs, 40 + s) for s in range(3)]   # dist R: the boolean witnesses share one bucket (a deep tree, trimmed early)
+    h = ctx.native(g16.R1CS.from_workload(cs, zs[0]).matrices)
+    bt = ctypes.c_void_p()
+    _chk(native, lib.mp_batch_create(h, 2, ctypes.byref(bt)))
+    rng = random.Random(77)
+    cases = [(rng.randrange(C.r), rng.randrange(C.r)), (0, 5), (5, 0), (C.r - 1, C.r - 1), (1, 1)]
+    for overlap in (1, 0):
+        _chk(native, lib.mp_batch_set_overlap(bt, overlap))
+        for count in (2, 1):
+            for ci, (r0, s0) in enumerate(cases):
+                idx = [(ci + j) % 3 for j in range(count)]
+                rs_ = [(r0 + j) % C.r for j in range(count)]
+                ss_ = [(s0 + 2 * j) % C.r for j in range(count)]
+                zb = native.pack_scalars([v for i in idx for v in zs[i]])
+                _chk(native, lib.mp_batch_upload(bt, count, zb, native.pack_scalars(rs_), native.pack_scalars(ss_)))
+                _chk(native, lib.mp_batch_run(bt, None))
+                out = ctypes.create_string_buffer(count * 192)
+                _chk(native, lib.mp_batch_download(bt, out))
+                for j in range(count):
+                    assert out.raw[j * 192:(j + 1) * 192] == trapdoor_proof_bytes(cs, trap, zs[idx[j]], rs_[j], ss_[j]), (overlap, count, ci, j)
+    lib.mp_batch_destroy(bt)
+    ctx.close()
 
 
 def test_batch_api_sync_async_and_serialised(native):
