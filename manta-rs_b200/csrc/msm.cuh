@@ -98,10 +98,11 @@ MsmGeom msm_geom_rc(const MsmGeom& g);
 int msm_rc_plan(const MsmGeom& g, const MsmSortWs& ws, const MsmGeom& g_rc, const MsmSortWs& ws_rc, size_t batch, cudaStream_t st);
 // Scratch of one batched-affine launch (all jobs x batch of the launch share one inversion tree per round).
 struct MsmBaWs {
-    void* prefix = nullptr;    // F per pair: thread-local prefix products of the denominators
+    void* prefix = nullptr;    // Fq per pair: thread-local prefix products of the denominators (G2: of their norms)
     uint32_t* desc = nullptr;  // 3 x u32 per pair: sources and destination
-    void* tot = nullptr;       // F per thread: product of its denominators, then its inverse
-    void* pre2 = nullptr;      // F per thread: second-level prefix products
+    void* tot = nullptr;       // Fq per thread: product of its denominators, then its inverse
+    void* pre2 = nullptr;      // Fq per thread: second-level prefix products
+    void* norm = nullptr;      // G2 only: Fq per pair, the norm of the denominator (forward pass -> backward pass)
     size_t cap_pairs = 0, cap_threads = 0;  // slots behind prefix/desc and tot/pre2 (sized for every count <= capacity)
     // Software pipeline over the slabs of a tree level (batches of more than 32 vectors): a SECOND scratch set of the same size,
     // so that the forward pass of slab i+1 and the backward pass of slab i-1 run while the latency-bound inversion kernel of
@@ -111,6 +112,7 @@ struct MsmBaWs {
     uint32_t* desc_b = nullptr;
     void* tot_b = nullptr;
     void* pre2_b = nullptr;
+    void* norm_b = nullptr;
     cudaStream_t mid_st[2] = {nullptr, nullptr};                               // side streams of k_ba_mid (owned by the caller)
     cudaEvent_t ev_fwd[2] = {nullptr, nullptr}, ev_mid[2] = {nullptr, nullptr};  // fwd done -> mid may start; mid done -> bwd may start
     mutable size_t dom_count = 0;           // vectors covered by the launch the ev_bwd0/1 events bracket (first slab of level 1)
