@@ -122,8 +122,9 @@ struct MsmBaWs {
     // optional: recorded around the round-1 k_ba_bwd launch of the bucket trees (the dominant kernel of a proof)
     cudaEvent_t ev_bwd0 = nullptr, ev_bwd1 = nullptr;
 };
-size_t msm_ba_ws_bytes(const MsmGeom* geoms, int n_jobs, size_t batch, bool g2);
-void msm_ba_ws_bind(MsmBaWs& ws, const MsmGeom* geoms, int n_jobs, size_t batch, bool g2, void* mem);
+// slab: vectors the scratch is sized for (0 = msm_ba_slab(batch); a caller with memory to spare passes more)
+size_t msm_ba_ws_bytes(const MsmGeom* geoms, int n_jobs, size_t batch, bool g2, size_t slab = 0);
+void msm_ba_ws_bind(MsmBaWs& ws, const MsmGeom* geoms, int n_jobs, size_t batch, bool g2, void* mem, size_t slab = 0);
 size_t msm_ba_slab(size_t batch, bool g2);   // vectors the round scratch of a batch of `batch` is sized for
 // host-only: {pairs, threads} a live `count` needs and {pairs, threads} a workspace sized for `cap` provides
 void msm_ba_ws_demand(const MsmGeom* geoms, int n_jobs, size_t cap, size_t count, uint64_t out[4]);

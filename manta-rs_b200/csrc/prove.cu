@@ -667,7 +667,14 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, size_t ac
             MP_TRY(b->pb_h.alloc(std::max(pbh, pbb2)));
             b->p_pb_h = b->p_pb_b2 = b->pb_h.p;
             MP_TRY(b->ba_mem_g1.alloc(std::max(std::max(ba1, ba2), 3 * wm)));
-            msm_ba_ws_bind(b->ba_g2, &b->gz, 1, cap, true, b->ba_mem_g1.p);
+            // the G2 rounds borrow the (larger) G1 round scratch: give them the largest slab of proofs that fits - fewer, larger
+            // launches per tree level
+            size_t g2_slab = cap;
+            while (g2_slab > msm_ba_slab(cap, true) && msm_ba_ws_bytes(&b->gz, 1, cap, true, g2_slab) > b->ba_mem_g1.bytes) g2_slab = (g2_slab + 1) / 2;
+            if (msm_ba_ws_bytes(&b->gz, 1, cap, true, g2_slab) > b->ba_mem_g1.bytes) g2_slab = 0;
+            if (const char* e = getenv("MP_G2_SLAB_DEFAULT"))
+                if (e[0] == '1') g2_slab = 0;   // A/B hook
+            msm_ba_ws_bind(b->ba_g2, &b->gz, 1, cap, true, b->ba_mem_g1.p, g2_slab);
             b->p_abc = b->ba_mem_g1.p;
             b->p_s1 = b->ba_mem_g1.as<char>() + wm;
             b->p_s2 = b->ba_mem_g1.as<char>() + 2 * wm;

@@ -1,0 +1,18 @@
+# G2 rounds in the largest slab that fits the aliased scratch; T threshold shifts; outputs under gpurun_out/r02t_*
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q -k "msm or reference_shapes or pipelined or latency_path or degenerate or more_than_one or outer_msm" > gpurun_out/r02t_pytest_subset.log 2>&1; tail -3 gpurun_out/r02t_pytest_subset.log
+B="--steps 5 --warmup 3 --no-single"
+timeout 600 python bench.py $B --parity-sample 4 > gpurun_out/r02t_bench_prove.json 2> gpurun_out/r02t_bench_prove.err; tail -c 300 gpurun_out/r02t_bench_prove.err
+MP_G2_SLAB_DEFAULT=1 timeout 600 python bench.py $B --no-cpu-baseline > gpurun_out/r02t_bench_g2slab_default.json 2>/dev/null
+MP_BA_T_SHIFT=1 timeout 600 python bench.py $B --no-cpu-baseline > gpurun_out/r02t_bench_tshift1.json 2>/dev/null
+MP_BA_T_SHIFT=-1 timeout 600 python bench.py $B --no-cpu-baseline > gpurun_out/r02t_bench_tshiftm1.json 2>/dev/null
+MP_BA_T_SHIFT=2 timeout 600 python bench.py $B --no-cpu-baseline > gpurun_out/r02t_bench_tshift2.json 2>/dev/null
+python - <<'PY'
+import json
+for n in ('prove','g2slab_default','tshift1','tshiftm1','tshift2'):
+    try:
+        d=json.load(open(f'gpurun_out/r02t_bench_{n}.json'))
+        print(n, round(d['value'],1), round(d['e2e']['value'],1), str(d['parity'])[:40], {k.split('(')[0]:round(v,2) for k,v in d['phase_ms_per_step_serialised'].items()}, d['device_bytes']['per_proof']>>20, d['gpu_launches'])
+    except Exception as e: print(n, 'ERR', e)
+PY
