@@ -225,6 +225,12 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.thread = None
+        self.t_begin = None
+
+    def begin(self):
+        """Marks the start of the timed region: nvidia-smi needs up to a second to come up on an 8-GPU box, so it is started
+        before the warm-up steps and only the samples that arrive after this mark are reported."""
+        self.t_begin = time.perf_counter()
 
     def start(self):
         try:
@@ -235,7 +241,7 @@ class ClockSampler:
 
         def pump():
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
 
@@ -247,7 +253,8 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        inside = [r for t, r in self.rows if self.t_begin is None or t >= self.t_begin]
+        for r in inside or [r for _, r in self.rows[-2:]]:   # a region shorter than the sampling period: the last samples before it ends
             try:
                 sm.append(float(r[1]))
                 mx = max(mx, float(r[2]))
@@ -476,13 +483,14 @@ def run_prove(args):
     # ---- device-resident throughput: W warm-up + K timed steps, assignments already in HBM
     for bh in batches:
         upload(bh)
+    sampler = ClockSampler(local_rank)
+    sampler.start()   # before the warm-up: the query process is up when the timed region starts
     for i in range(args.warmup):
         run(batches[i % NB])
-    sampler = ClockSampler(local_rank)
     nphase = 8
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    sampler.start()
+    sampler.begin()
     t0 = time.perf_counter()
     ev0.record()
     for k in range(args.steps):
@@ -685,13 +693,14 @@ def run_single(args):
     rb, sb_ = [nat.pack_scalars([r]) for r in rs], [nat.pack_scalars([s]) for s in ss]
     out = ctypes.create_string_buffer(192)
     proofs = {}
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(max(args.warmup, 3)):
         nat.check(lib.mp_prove(ctx, zb[i % 4], rb[i % 4], sb_[i % 4], out))
-    sampler = ClockSampler(local_rank)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler.start()
+    sampler.begin()
     lat = []
     t_all = time.perf_counter()
     for k in range(args.steps):
@@ -899,13 +908,14 @@ def run_g2_stress(args):
         nat.check(sum_fn(local_rank, stacked, world, out))
         return out.raw, ms.value
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(local_rank)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler.start()
+    sampler.begin()
     devs, result = [], None
     t0 = time.perf_counter()
     for _ in range(args.steps):
