@@ -648,7 +648,9 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, size_t ac
     MP_TRY(b->h_canon.alloc(cap * m * 32));
     b->gz = msm_geom(PROVE_C, 1, c->zlen, c->zlen, cap * 2);  // G1 launches carry 4 jobs, the G2 launch one
     b->gh = msm_geom(PROVE_C, 1, (uint32_t)c->m, (uint32_t)c->m, cap * 2);
-    const bool ext = msm_use_batched_affine() && cap <= 2;   // the A and B lists also carry the scaled vectors (see `zx`)
+    // MP_LADDERS_AS_MSM=1 (measured alternative, off by default): the A and B lists also carry the scaled vectors (see `zx`)
+    bool ext = false;
+    if (const char* e = getenv("MP_LADDERS_AS_MSM")) ext = e[0] == '1' && msm_use_batched_affine() && cap <= 2;
     MP_TRY(msm_sort_ws_alloc(b->sort_a, b->gz, ext ? 2 * cap : cap, b->sort_a_mem));
     MP_TRY(msm_sort_ws_alloc(b->sort_b, b->gz, ext ? 2 * cap : cap, b->sort_b_mem));
     MP_TRY(msm_sort_ws_alloc(b->sort_l, b->gz, cap, b->sort_l_mem));
@@ -692,12 +694,14 @@ static int batch_create_impl(mp_ctx* c, size_t cap, int high_priority, size_t ac
             MP_TRY(b->ba_mem_h.alloc(msm_ba_ws_bytes(&b->gh, 1, cap, false)));
             msm_ba_ws_bind(b->ba_h, &b->gh, 1, cap, false, b->ba_mem_h.p);
             MP_TRY(b->lad.alloc(cap * 2 * XYZZ<Fq>::WORDS * 4));
-            const MsmGeom geoms_abl[5] = {b->gz, b->gz, b->gz, b->gz, b->gz};
-            MP_TRY(b->ba_mem_abl.alloc(msm_ba_ws_bytes(geoms_abl, 5, cap, false)));
-            msm_ba_ws_bind(b->ba_abl, geoms_abl, 5, cap, false, b->ba_mem_abl.p);
-            MP_TRY(b->zx.alloc(3 * cap * c->zlen * 32));
-            MP_TRY(b->red_sa.alloc(msm_reduce_scratch_bytes(b->gz, cap, false)));
-            MP_TRY(b->red_rb.alloc(msm_reduce_scratch_bytes(b->gz, cap, false)));
+            if (ext) {
+                const MsmGeom geoms_abl[5] = {b->gz, b->gz, b->gz, b->gz, b->gz};
+                MP_TRY(b->ba_mem_abl.alloc(msm_ba_ws_bytes(geoms_abl, 5, cap, false)));
+                msm_ba_ws_bind(b->ba_abl, geoms_abl, 5, cap, false, b->ba_mem_abl.p);
+                MP_TRY(b->zx.alloc(3 * cap * c->zlen * 32));
+                MP_TRY(b->red_sa.alloc(msm_reduce_scratch_bytes(b->gz, cap, false)));
+                MP_TRY(b->red_rb.alloc(msm_reduce_scratch_bytes(b->gz, cap, false)));
+            }
         }
         b->ba_g1.ev_bwd0 = b->ev_dom0;
         b->ba_g1.ev_bwd1 = b->ev_dom1;
