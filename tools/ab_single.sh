@@ -1,14 +1,14 @@
-# A/B of the single-proof latency path on one B200; outputs under gpurun_out/r02q_*
+# A/B of the single-proof latency path on one B200 (switch names as of the final tree; the r02q_* artifacts were taken when the MSM form of the ladders and two trimmed levels were the defaults); outputs under gpurun_out/r02q_*
 set -x
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r02q_pytest_gpu.log 2>&1; tail -5 gpurun_out/r02q_pytest_gpu.log
 S="--workload single --no-cpu-baseline"
-timeout 300 python bench.py $S > gpurun_out/r02q_single_new.json 2> gpurun_out/r02q_single_new.err; tail -c 300 gpurun_out/r02q_single_new.err
+MP_LADDERS_AS_MSM=1 MP_BA_TRIM_LEVELS=2 timeout 300 python bench.py $S > gpurun_out/r02q_single_new.json 2> gpurun_out/r02q_single_new.err; tail -c 300 gpurun_out/r02q_single_new.err
 MP_SMALL_PATH_OLD=1 MP_BA_TRIM_LEVELS=0 timeout 300 python bench.py $S > gpurun_out/r02q_single_old.json 2>/dev/null
-MP_MSM_LADDERS=0 timeout 300 python bench.py $S > gpurun_out/r02q_single_ladders.json 2>/dev/null
-MP_BA_TRIM_LEVELS=0 timeout 300 python bench.py $S > gpurun_out/r02q_single_trim0.json 2>/dev/null
-MP_BA_TRIM_LEVELS=1 timeout 300 python bench.py $S > gpurun_out/r02q_single_trim1.json 2>/dev/null
-MP_BA_TRIM_LEVELS=3 timeout 300 python bench.py $S > gpurun_out/r02q_single_trim3.json 2>/dev/null
+MP_BA_TRIM_LEVELS=2 timeout 300 python bench.py $S > gpurun_out/r02q_single_ladders.json 2>/dev/null
+MP_LADDERS_AS_MSM=1 MP_BA_TRIM_LEVELS=0 timeout 300 python bench.py $S > gpurun_out/r02q_single_trim0.json 2>/dev/null
+MP_LADDERS_AS_MSM=1 MP_BA_TRIM_LEVELS=1 timeout 300 python bench.py $S > gpurun_out/r02q_single_trim1.json 2>/dev/null
+MP_LADDERS_AS_MSM=1 MP_BA_TRIM_LEVELS=3 timeout 300 python bench.py $S > gpurun_out/r02q_single_trim3.json 2>/dev/null
 timeout 300 python bench.py --workload msm_sweep --no-cpu-baseline --max-log 20 > gpurun_out/r02q_msm_sweep.json 2>/dev/null
 for f in gpurun_out/r02q_single_*.json; do python - "$f" <<'PY'
 import json,sys
