@@ -121,3 +121,34 @@ def test_glv_constants_of_the_finishing_kernel():
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "manta-rs_b200", "csrc", "bls12_381_constants.cuh")).read()
     mont = beta * (1 << 384) % C.q
     assert "FQ_GLV_BETA[12] = {" + ", ".join("0x%08xu" % ((mont >> (32 * i)) & 0xFFFFFFFF) for i in range(12)) + "}" in hdr
+
+
+def test_shared_inversion_of_g2_chords_through_norms():
+    """The algebra of the G2 batched-affine rounds (msm_impl.inc BaInv<Fq2>): the denominators x2 - x1 of a set of
+    Fq2 chord additions are inverted through ONE Fq inversion of the product of their norms - forward prefix products of
+    a^2 + b^2, back-substitution, 1/d = conj(d) * n^-1 - and the chord formula with those inverses equals the group law."""
+    import random
+    from oracle.pyref.fields import BLS12_381 as C, fq2_sub, fq2_mul, fq2_sqr, fq2_conj, fq2_scalar
+    from oracle.pyref.curves import Group
+    G = Group(C, 2)
+    q = C.q
+    rng = random.Random(41)
+    pts = [G.mul(G.gen, rng.randrange(1, C.r)) for _ in range(12)]
+    pairs = [(pts[2 * i], pts[2 * i + 1]) for i in range(6)]
+    d = [fq2_sub(q, b[0], a[0]) for a, b in pairs]
+    norms = [(x[0] * x[0] + x[1] * x[1]) % q for x in d]
+    prefix, run = [], 1
+    for n in norms:                       # k_ba_fwd: running product of the norms
+        run = run * n % q
+        prefix.append(run)
+    inv = pow(run, -1, q)                 # k_ba_mid: the only inversion, in Fq
+    for t in range(len(pairs) - 1, -1, -1):   # k_ba_bwd
+        ninv = inv * prefix[t - 1] % q if t else inv
+        inv = inv * norms[t] % q
+        dinv = fq2_scalar(q, fq2_conj(q, d[t]), ninv)
+        assert fq2_mul(q, dinv, d[t]) == (1, 0)
+        (x1, y1), (x2, y2) = pairs[t]
+        lam = fq2_mul(q, fq2_sub(q, y2, y1), dinv)
+        x3 = fq2_sub(q, fq2_sub(q, fq2_sqr(q, lam), x1), x2)
+        y3 = fq2_sub(q, fq2_mul(q, lam, fq2_sub(q, x1, x3)), y1)
+        assert (x3, y3) == G.add(pairs[t][0], pairs[t][1])
