@@ -45,3 +45,26 @@ def test_main_arm_line_small_batch():
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(rf) and 0 < rf["frac"] < 1.2
     cb = d["cpu_baseline"]
     assert {"value", "unit", "cores", "kind", "sample"} <= set(cb) and cb["kind"] == "port"
+
+
+def test_clock_sampler_reports_the_samples_of_the_timed_region():
+    """bench.py starts nvidia-smi before the warm-up (it needs up to a second to come up on an 8-GPU box) and reports the samples
+    that arrive after `begin()`; a region shorter than the sampling period falls back to the last samples before it ended."""
+    import importlib.util
+    import time
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    row = lambda mhz, cap: ["0", str(mhz), "1965", "700", "Not Active", "Not Active", "Not Active", cap]
+    s = bench.ClockSampler(0)
+    t0 = time.perf_counter()
+    s.rows = [(t0 - 2.0, row(345, "Not Active")), (t0 - 1.0, row(1200, "Not Active"))]   # idle and warm-up samples
+    s.begin()
+    s.rows += [(time.perf_counter() + 0.1, row(1965, "Active")), (time.perf_counter() + 0.2, row(1950, "Not Active"))]
+    out = s.stop()
+    assert out["samples"] == 2 and out["sm_mhz"] == 1957.5 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+    s2 = bench.ClockSampler(0)
+    s2.rows = [(t0 - 2.0, row(345, "Not Active")), (t0 - 1.0, row(1965, "Not Active"))]
+    s2.begin()
+    out2 = s2.stop()   # nothing arrived inside the region: the last samples before it ended
+    assert out2["samples"] == 2 and out2["sm_mhz"] == 1965.0
